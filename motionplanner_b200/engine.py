@@ -1,0 +1,164 @@
+"""Host-side handle of the device-resident collision checker (one per GPU).
+
+Thin numpy <-> C-ABI glue; every geometric decision is made by the CUDA kernels in csrc/mpc_kernels.cu.
+Reference being replaced: the per-occupancy shapely loop of ``collision_check``
+(src/lowLevelPlannerManeuverAutomaton.py:95-125) and ``collisionChecker`` (auxiliary/collisionChecker.py:6-35).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import (MODE_COUNT_WORK, MODE_NO_CULL, MODE_NO_EARLY_EXIT, MODE_PLANNER, MODE_VALIDATOR, QUERY_DTYPE,
+                    MpcError)
+
+__all__ = ["CollisionEngine", "QUERY_DTYPE", "MODE_PLANNER", "MODE_VALIDATOR", "MODE_NO_CULL", "MODE_NO_EARLY_EXIT",
+           "MODE_COUNT_WORK", "MpcError", "make_queries", "unpack_mask"]
+
+
+def _arr(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def make_queries(n):
+    q = np.zeros(n, dtype=QUERY_DTYPE)
+    q["c"] = 1.0
+    q["step_limit"] = 2 ** 30
+    return q
+
+
+def mask_words(queries):
+    return int(((queries["cand_cnt"].astype(np.int64) + 31) // 32).sum())
+
+
+def unpack_mask(mask, queries):
+    """packed device mask -> flat uint8 array (1 = candidate collides) in query order"""
+    out = np.zeros(int(queries["cand_cnt"].sum()), dtype=np.uint8)
+    w = o = 0
+    for cnt in queries["cand_cnt"]:
+        nw = (int(cnt) + 31) // 32
+        bits = np.unpackbits(mask[w:w + nw].view(np.uint8), bitorder="little")[:cnt]
+        out[o:o + cnt] = bits
+        w += nw
+        o += cnt
+    return out
+
+
+class CollisionEngine:
+    """one context = one GPU + one stream (see include/mpc.h)"""
+
+    def __init__(self, device=0):
+        self._L = _cabi.load()
+        self._ctx = C.c_void_p()
+        rc = self._L.mpc_create(int(device), C.byref(self._ctx))
+        if rc != 0:
+            msg = self._L.mpc_last_error(self._ctx).decode() if self._ctx else "mpc_create failed"
+            if self._ctx:
+                self._L.mpc_destroy(self._ctx)
+                self._ctx = C.c_void_p()
+            raise MpcError("mpc_create(device=%d) -> %d: %s" % (device, rc, msg))
+        self.device = int(device)
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._L.mpc_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise MpcError("%s -> %d: %s" % (what, rc, self._L.mpc_last_error(self._ctx).decode()))
+
+    def device_info(self):
+        info = _cabi.DevInfo()
+        self._check(self._L.mpc_device_info(self._ctx, C.byref(info)), "mpc_device_info")
+        return dict(name=info.name.decode(), sm_count=info.sm_count, cc=(info.cc_major, info.cc_minor),
+                    clock_khz=info.clock_khz, global_mem=info.global_mem, l2_bytes=info.l2_bytes,
+                    abi_version=info.abi_version)
+
+    # -- library -------------------------------------------------------------------------------------------------
+    def upload_library(self, verts, nv, tidx, set_off=None, set_idx=None):
+        """verts [P,J,V,2] f8, nv [P,J] i4 (0 = unused slot), tidx [P,J] i4; optional candidate sets (CSR)"""
+        verts = _arr(verts, np.float64)
+        nv = _arr(nv, np.int32)
+        tidx = _arr(tidx, np.int32)
+        P, J, V = verts.shape[0], verts.shape[1], verts.shape[2]
+        assert verts.shape == (P, J, V, 2) and nv.shape == (P, J) and tidx.shape == (P, J)
+        nsets = 0
+        if set_off is not None:
+            set_off = _arr(set_off, np.int32)
+            set_idx = _arr(set_idx, np.int32)
+            nsets = len(set_off) - 1
+        self._check(self._L.mpc_upload_library(self._ctx, _cabi.ptr(verts), _cabi.ptr(nv), _cabi.ptr(tidx), P, J, V,
+                                               _cabi.ptr(set_off) if nsets else None,
+                                               _cabi.ptr(set_idx) if nsets else None, nsets), "mpc_upload_library")
+        self.P, self.J = P, J
+
+    # -- scenes --------------------------------------------------------------------------------------------------
+    def set_scenes(self, scene_step_off, origins, step_obst_off, obst, obst_nv, step_seg_begin, step_seg_end, segs):
+        scene_step_off = _arr(scene_step_off, np.int32)
+        nscenes = len(scene_step_off) - 1
+        origins = _arr(origins, np.float64).reshape(nscenes, 2)
+        step_obst_off = _arr(step_obst_off, np.int32)
+        nsteps = int(scene_step_off[-1])
+        assert len(step_obst_off) == nsteps + 1
+        obst = _arr(obst if obst is not None else np.zeros((0, 4, 2)), np.float64)
+        if obst.ndim != 3:
+            obst = obst.reshape(-1, 4, 2)
+        obst_nv = _arr(obst_nv if obst_nv is not None else np.zeros(0), np.int32)
+        assert len(obst_nv) == obst.shape[0] == int(step_obst_off[-1])
+        step_seg_begin = _arr(step_seg_begin, np.int32)
+        step_seg_end = _arr(step_seg_end, np.int32)
+        assert len(step_seg_begin) == len(step_seg_end) == nsteps
+        segs = _arr(segs if segs is not None else np.zeros((0, 4)), np.float64).reshape(-1, 4)
+        self._check(self._L.mpc_set_scenes(self._ctx, nscenes, _cabi.ptr(scene_step_off), _cabi.ptr(origins),
+                                           _cabi.ptr(step_obst_off), _cabi.ptr(obst), _cabi.ptr(obst_nv),
+                                           int(obst.shape[1]), _cabi.ptr(step_seg_begin), _cabi.ptr(step_seg_end),
+                                           _cabi.ptr(segs), len(segs)), "mpc_set_scenes")
+
+    # -- queries -------------------------------------------------------------------------------------------------
+    def query_mask(self, queries, cand_idx=None, mode=MODE_PLANNER):
+        """returns (packed uint32 mask, stats dict): bit = 1 iff the candidate collides"""
+        queries = _arr(queries, QUERY_DTYPE)
+        cand = _arr(cand_idx, np.int32) if cand_idx is not None else np.zeros(0, np.int32)
+        nw = mask_words(queries)
+        mask = np.zeros(max(nw, 1), dtype=np.uint32)
+        st = _cabi.Stats()
+        self._check(self._L.mpc_query(self._ctx, len(queries), _cabi.ptr(queries), _cabi.ptr(cand), len(cand),
+                                      int(mode), _cabi.ptr(mask), nw, C.byref(st)), "mpc_query")
+        return mask[:nw], st.as_dict()
+
+    def query(self, queries, cand_idx=None, mode=MODE_PLANNER):
+        """returns (uint8 [sum cand_cnt] 1 = collides, stats dict)"""
+        queries = _arr(queries, QUERY_DTYPE)
+        mask, st = self.query_mask(queries, cand_idx, mode)
+        return unpack_mask(mask, queries), st
+
+    # -- measurement (bench.py) ------------------------------------------------------------------------------------
+    def prepare(self, queries, cand_idx=None, mode=MODE_PLANNER):
+        queries = _arr(queries, QUERY_DTYPE)
+        cand = _arr(cand_idx, np.int32) if cand_idx is not None else np.zeros(0, np.int32)
+        self._check(self._L.mpc_prepare_query(self._ctx, len(queries), _cabi.ptr(queries), _cabi.ptr(cand), len(cand),
+                                              int(mode)), "mpc_prepare_query")
+        self._prepared = queries
+
+    def run_prepared(self, iters, flush_l2=True):
+        """returns (ms_total [iters], ms_main [iters], stats) -- device times from CUDA events around the kernels"""
+        ms_total = np.zeros(max(iters, 1), np.float32)
+        ms_main = np.zeros(max(iters, 1), np.float32)
+        st = _cabi.Stats()
+        self._check(self._L.mpc_run_prepared(self._ctx, int(iters), int(bool(flush_l2)), _cabi.ptr(ms_total),
+                                             _cabi.ptr(ms_main), C.byref(st)), "mpc_run_prepared")
+        return ms_total[:iters], ms_main[:iters], st.as_dict()
+
+    def fetch(self):
+        nw = mask_words(self._prepared)
+        mask = np.zeros(max(nw, 1), dtype=np.uint32)
+        self._check(self._L.mpc_fetch_mask(self._ctx, _cabi.ptr(mask), nw), "mpc_fetch_mask")
+        return unpack_mask(mask[:nw], self._prepared)

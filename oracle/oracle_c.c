@@ -273,6 +273,15 @@ static int check_candidate(const orc_problem_t *pb, const orc_query_t *q, int p,
     int collide = 0;
     int s0 = pb->scene_step_off[q->scene];
     int nsteps = pb->scene_step_off[q->scene + 1] - s0;
+    /* nominal work of this candidate, independent of the early return */
+    for (int j = 0; j < pb->J; j++) {
+        if (pb->lib_nv[(size_t)p * pb->J + j] <= 0) continue;
+        int t = q->t0 + pb->lib_tidx[(size_t)p * pb->J + j];
+        if (t > q->step_limit || t < 0 || t >= nsteps) continue;
+        int step = s0 + t;
+        st->pairs_nominal += pb->step_obst_off[step + 1] - pb->step_obst_off[step];
+        if (pb->step_seg_begin[step] >= 0) st->pairs_nominal += pb->step_seg_end[step] - pb->step_seg_begin[step];
+    }
     for (int j = 0; j < pb->J; j++) {
         int nv = pb->lib_nv[(size_t)p * pb->J + j];
         if (nv <= 0) continue;
@@ -293,7 +302,6 @@ static int check_candidate(const orc_problem_t *pb, const orc_query_t *q, int p,
         int o0 = pb->step_obst_off[step], o1 = pb->step_obst_off[step + 1];
         int g0 = pb->step_seg_begin[step], g1 = pb->step_seg_end[step];
         int nseg = (g0 >= 0) ? (g1 - g0) : 0;
-        st->pairs_nominal += (o1 - o0) + nseg;
         int bad = 0;
         /* road / free-space boundary */
         if (g0 >= 0) {

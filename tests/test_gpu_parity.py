@@ -1,0 +1,253 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, include/mpc.h) against the float64 exact-sign oracle on
+the same seeded inputs.  Bar: bit-exact decisions (the path is boolean); the only tolerated source of disagreement
+would be contacts closer than 1e-9 m, and those are counted -- the assertions below demand zero disagreements."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from motionplanner_b200 import workloads as W
+from motionplanner_b200.engine import (MODE_COUNT_WORK, MODE_NO_CULL, MODE_NO_EARLY_EXIT, MODE_PLANNER, MODE_VALIDATOR,
+                                       CollisionEngine, MpcError, make_queries)
+from oracle import oracle as orc
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = CollisionEngine(0)
+    yield e
+    e.close()
+
+
+def stage(eng, lib, sc, origins):
+    eng.upload_library(lib["verts"], lib["nv"], lib["tidx"], lib.get("set_off"), lib.get("set_idx"))
+    eng.set_scenes(sc["scene_step_off"], origins, sc["step_obst_off"], sc["obst"], sc["obst_nv"],
+                   sc["step_seg_begin"], sc["step_seg_end"], sc["segs"])
+
+
+def both(eng, lib, sc, origins, q, cand=None, mode=0):
+    stage(eng, lib, sc, origins)
+    got, st = eng.query(q, cand, mode)
+    omode = (orc.MODE_STRICT if mode & MODE_VALIDATOR else 0) | orc.MODE_NO_EARLY_EXIT
+    want, ost = orc.Problem(lib, sc).check(q, cand, omode)
+    return got, want, st, ost
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("mode", [MODE_PLANNER, MODE_VALIDATOR])
+def test_adversarial_rectangles(eng, seed, mode):
+    lib, sc, org, q = W.adversarial_problem(seed)
+    got, want, st, ost = both(eng, lib, sc, org, q, None, mode)
+    assert np.array_equal(got, want), "disagreements: %d" % (got != want).sum()
+    assert st["pairs_nominal"] == ost["pairs_nominal"]
+    assert 0 < want.mean() < 1                     # the problem exercises both outcomes
+    assert st["refined_fp64"] > 0                  # near-contacts really went through the float64 pass
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_adversarial_far_from_origin(eng, seed):
+    """|coordinates| like the bundled scenarios (up to 1.4 km): the scene origin keeps float32 local"""
+    lib, sc, org, q = W.adversarial_problem(100 + seed, offset=(1421.0, -677.0))
+    for mode in (MODE_PLANNER, MODE_VALIDATOR):
+        got, want, st, _ = both(eng, lib, sc, org, q, None, mode)
+        assert np.array_equal(got, want)
+    # a badly chosen origin only widens the band, it must not change a decision
+    got, want, st2, _ = both(eng, lib, sc, np.zeros((1, 2)), q, None, MODE_PLANNER)
+    assert np.array_equal(got, want)
+    assert st2["tau"] > st["tau"]
+
+
+@pytest.mark.parametrize("lib_verts,obst_verts", [(4, 8), (8, 4), (12, 8), (16, 3)])
+def test_adversarial_general_polygons(eng, lib_verts, obst_verts):
+    for seed in range(2):
+        lib, sc, org, q = W.adversarial_problem(200 + seed, lib_verts=lib_verts, obst_verts=obst_verts)
+        for mode in (MODE_PLANNER, MODE_VALIDATOR):
+            got, want, st, _ = both(eng, lib, sc, org, q, None, mode)
+            assert np.array_equal(got, want), (lib_verts, obst_verts, seed, mode)
+
+
+def test_mode_flags_do_not_change_decisions(eng):
+    lib, sc, org, q = W.adversarial_problem(7, P=200, max_obst=70)
+    stage(eng, lib, sc, org)
+    base, st0 = eng.query(q, None, MODE_PLANNER)
+    for m in (MODE_NO_CULL, MODE_NO_EARLY_EXIT, MODE_NO_CULL | MODE_NO_EARLY_EXIT, MODE_COUNT_WORK,
+              MODE_COUNT_WORK | MODE_NO_EARLY_EXIT | MODE_NO_CULL):
+        got, st = eng.query(q, None, m)
+        assert np.array_equal(got, base), m
+    # instrumented launch: without culling or exits every nominal pair runs the full axis test
+    assert st["axis_tests"] == st["pairs_nominal"]
+    got, st = eng.query(q, None, MODE_COUNT_WORK | MODE_NO_EARLY_EXIT)
+    assert st["cull_tests"] == st["pairs_nominal"] and 0 < st["axis_tests"] < st["pairs_nominal"]
+
+
+def test_explicit_candidate_lists_and_sets(eng):
+    lib, sc, org, q = W.adversarial_problem(11)
+    stage(eng, lib, sc, org)
+    P = lib["verts"].shape[0]
+    rng = np.random.default_rng(0)
+    cand = rng.permutation(P).astype(np.int32)[:70]
+    q2 = q.copy()
+    q2["cand_set"] = -1
+    q2["cand_off"] = [0, 10, 33]
+    q2["cand_cnt"] = [10, 23, 37]
+    got, _ = eng.query(q2, cand, MODE_PLANNER)
+    want, _ = orc.Problem(lib, sc).check(q2, cand, orc.MODE_NO_EARLY_EXIT)
+    assert np.array_equal(got, want)
+    # permutation equivariance: decisions follow the candidates
+    q3 = q[:1].copy()
+    q3["cand_set"] = -1
+    q3["cand_off"] = 0
+    q3["cand_cnt"] = P
+    a, _ = eng.query(q3, np.arange(P, dtype=np.int32), MODE_PLANNER)
+    perm = rng.permutation(P).astype(np.int32)
+    b, _ = eng.query(q3, perm, MODE_PLANNER)
+    assert np.array_equal(a[perm], b)
+
+
+def test_time_index_guards(eng):
+    """reference guards (src/lowLevelPlannerManeuverAutomaton.py:120,122): ind+time <= param['steps'] and
+    ind+time < len(space); skipped occupancies count as free"""
+    lib, sc, org, q = W.adversarial_problem(3)
+    stage(eng, lib, sc, org)
+    nsteps = int(sc["scene_step_off"][1])
+    for t0, lim in ((nsteps, 99), (nsteps - 1, 99), (0, 0), (0, -1), (2, 3), (-3, 99)):
+        qq = q.copy()
+        qq["t0"], qq["step_limit"] = t0, lim
+        got, _ = eng.query(qq, None, MODE_PLANNER)
+        want, _ = orc.Problem(lib, sc).check(qq, None, orc.MODE_NO_EARLY_EXIT)
+        assert np.array_equal(got, want), (t0, lim)
+    qq = q.copy()
+    qq["t0"] = nsteps
+    got, _ = eng.query(qq, None, MODE_PLANNER)
+    assert got.sum() == 0                      # everything beyond the horizon: nothing is tested
+
+
+def test_empty_and_ragged_inputs(eng):
+    lib, sc, org, q = W.adversarial_problem(4)
+    stage(eng, lib, sc, org)
+    # empty batch, empty candidate list
+    got, st = eng.query(make_queries(0), None, MODE_PLANNER)
+    assert got.size == 0
+    qq = q.copy()
+    qq["cand_cnt"] = [0, 5, 0]
+    got, _ = eng.query(qq, None, MODE_PLANNER)
+    want, _ = orc.Problem(lib, sc).check(qq, None, orc.MODE_NO_EARLY_EXIT)
+    assert got.size == 5 and np.array_equal(got, want)
+    # scene without obstacles and without region: everything free
+    nsteps = 4
+    sc0 = dict(scene_step_off=np.array([0, nsteps], np.int32), step_obst_off=np.zeros(nsteps + 1, np.int32),
+               obst=np.zeros((0, 4, 2)), obst_nv=np.zeros(0, np.int32), step_seg_begin=np.full(nsteps, -1, np.int32),
+               step_seg_end=np.full(nsteps, -1, np.int32), segs=np.zeros((0, 4)))
+    stage(eng, lib, sc0, org)
+    got, st = eng.query(q, None, MODE_PLANNER)
+    assert got.sum() == 0 and st["pairs_nominal"] == 0
+    # empty region at every step: nothing is contained (shapely: empty.contains(x) is False)
+    sc0["step_seg_begin"][:] = 0
+    sc0["step_seg_end"][:] = 0
+    stage(eng, lib, sc0, org)
+    got, _ = eng.query(q, None, MODE_PLANNER)
+    want, _ = orc.Problem(lib, sc0).check(q, None, orc.MODE_NO_EARLY_EXIT)
+    assert np.array_equal(got, want) and got.sum() > 0
+
+
+def test_many_obstacles_and_segments_multi_phase(eng):
+    """more obstacles / segments per step than one shared-memory tile holds"""
+    rng = np.random.default_rng(5)
+    lib, sc, org, q = W.adversarial_problem(9, P=64, nsteps=3, max_obst=4)
+    nsteps = 3
+    O = 700
+    obst = W.rect_vertices(rng.uniform(-70, 70, (nsteps, O)), rng.uniform(-70, 70, (nsteps, O)),
+                           rng.uniform(-3, 3, (nsteps, O)), 1.0, 0.5).reshape(-1, 4, 2)
+    sc["obst"], sc["obst_nv"] = obst, np.full(nsteps * O, 4, np.int32)
+    sc["step_obst_off"] = (np.arange(nsteps + 1) * O).astype(np.int32)
+    # a many-sided ring (1200 segments) as the region
+    n = 1200
+    ang = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    ring = np.stack([75 * np.cos(ang), 75 * np.sin(ang)], -1)
+    sc["segs"] = np.concatenate([ring, np.roll(ring, -1, axis=0)], axis=1)
+    sc["step_seg_begin"] = np.zeros(nsteps, np.int32)
+    sc["step_seg_end"] = np.full(nsteps, n, np.int32)
+    for mode in (MODE_PLANNER, MODE_NO_EARLY_EXIT):
+        got, want, st, ost = both(eng, lib, sc, org, q, None, mode)
+        assert np.array_equal(got, want)
+        assert st["pairs_nominal"] == ost["pairs_nominal"]
+    assert 0 < want.mean() < 1
+
+
+def test_multiple_scenes_in_one_batch(eng):
+    parts = [W.adversarial_problem(300 + i, P=64, nsteps=5 + i, offset=(200.0 * i, -90.0 * i)) for i in range(4)]
+    lib = parts[0][0]
+    sso, soo, obst, onv, sb, se, segs, orgs, qs = [0], [0], [], [], [], [], [], [], []
+    for i, (_, sc, org, q) in enumerate(parts):
+        nseg0 = sum(len(s) for s in segs)
+        sso.append(sso[-1] + int(sc["scene_step_off"][1]))
+        soo.extend((sc["step_obst_off"][1:] + soo[-1]).tolist())
+        obst.append(sc["obst"]); onv.append(sc["obst_nv"])
+        sb.extend([b + nseg0 if b >= 0 else -1 for b in sc["step_seg_begin"]])
+        se.extend([e + nseg0 if e >= 0 else -1 for e in sc["step_seg_end"]])
+        segs.append(sc["segs"]); orgs.append(org[0])
+        q = q.copy(); q["scene"] = i
+        qs.append(q)
+    sc = dict(scene_step_off=np.array(sso, np.int32), step_obst_off=np.array(soo, np.int32),
+              obst=np.concatenate(obst), obst_nv=np.concatenate(onv), step_seg_begin=np.array(sb, np.int32),
+              step_seg_end=np.array(se, np.int32), segs=np.concatenate(segs))
+    q = np.concatenate(qs)
+    got, want, st, ost = both(eng, lib, sc, np.array(orgs), q, None, MODE_PLANNER)
+    assert np.array_equal(got, want)
+    # per-scene results equal the single-scene results
+    o = 0
+    for i, (lib_i, sc_i, org_i, q_i) in enumerate(parts):
+        w, _ = orc.Problem(lib, sc_i).check(q_i, None, orc.MODE_NO_EARLY_EXIT)
+        n = int(q_i["cand_cnt"].sum())
+        assert np.array_equal(got[o:o + n], w)
+        o += n
+
+
+def test_c4_dense_traffic_full_size(eng):
+    """BASELINE.json configs[3] at full size (4096 x 256 x 50 = 52.4 M pairs per query) against the oracle, plus
+    size-independent properties: idempotence and invariance under an exact rigid motion of the whole problem"""
+    lib, sc, org, q = W.c4_problem(nqueries=3)
+    stage(eng, lib, sc, org)
+    got, st = eng.query(q, None, MODE_PLANNER)
+    want, ost = orc.Problem(lib, sc).check(q, None, 0, inner_parallel=True)     # reference early return: same decisions
+    assert st["pairs_nominal"] == 3 * 4096 * 50 * (256 + 4) == ost["pairs_nominal"]
+    assert np.array_equal(got, want)
+    again, _ = eng.query(q, None, MODE_PLANNER)
+    assert np.array_equal(got, again)
+    # rotate the world by exactly 90 degrees about the origin and shift by integers: (x, y) -> (-y + 64, x - 32)
+    rot = lambda a: np.stack([-a[..., 1] + 64.0, a[..., 0] - 32.0], -1)
+    sc2 = dict(sc)
+    sc2["obst"] = rot(sc["obst"])
+    sc2["segs"] = np.concatenate([rot(sc["segs"][:, 0:2]), rot(sc["segs"][:, 2:4])], axis=1)
+    q2 = q.copy()
+    q2["x"], q2["y"] = -q["y"] + 64.0, q["x"] - 32.0
+    q2["c"], q2["s"] = -q["s"], q["c"]
+    stage(eng, lib, sc2, rot(org))
+    got2, _ = eng.query(q2, None, MODE_PLANNER)
+    # the rotation of the pose is exact only up to the rounding of the products, so compare through the oracle too
+    want2, _ = orc.Problem(lib, sc2).check(q2, None, 0, inner_parallel=True)
+    assert np.array_equal(got2, want2)
+    assert (got2 != got).mean() < 1e-3
+
+
+def test_error_behaviour(eng):
+    e2 = CollisionEngine(0)
+    with pytest.raises(MpcError):
+        e2.query(make_queries(1), None, 0)                       # nothing staged
+    lib, sc, org, q = W.adversarial_problem(1)
+    stage(e2, lib, sc, org)
+    bad = q.copy()
+    bad["scene"] = 5
+    with pytest.raises(MpcError):
+        e2.query(bad, None, 0)
+    bad = q.copy()
+    bad["cand_set"] = -1
+    with pytest.raises(MpcError):
+        e2.query(bad, np.array([0, 1, 10 ** 6], np.int32), 0)
+    tid = lib["tidx"].copy()
+    tid[3, 2] += 1
+    with pytest.raises(MpcError):
+        e2.upload_library(lib["verts"], lib["nv"], tid)          # irregular slot must be re-slotted by the caller
+    with pytest.raises(MpcError):
+        CollisionEngine(99)
+    e2.close()
