@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched motion-primitive collision check (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--queries Q]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[3] "synthetic dense traffic: 4096 primitives x 256 obstacles x 50
+timesteps per query, 1 GPU" (seeds 0/1/2).  A *step* is one pass of the hot path over one batch of Q
+such queries (Q ego poses with jitter against the same predicted scene, all 4096 candidates each).  One *check* is one
+(primitive occupancy, obstacle, time step) pair decided, so a step is Q x 4096 x 256 x 50 checks; the 4 road-boundary
+segments per (primitive, step) are decided too but not counted.
+
+  value   device-resident throughput: scene, library and queries already in HBM, CUDA-event time of every kernel of
+          the step (memsets + k_check + k_refine), L2 flushed before every timed step.
+  e2e     same metric through the public call a user makes (CollisionEngine.set_scenes + .query, i.e. mpc_set_scenes +
+          mpc_query of include/mpc.h) with HOST numpy buffers: per step the float64 obstacle prediction and the poses
+          go host->device and the packed result mask comes back, all inside the timed region.
+  N > 1   one process per GPU, replicated library, independent queries per rank (weak scaling), no collective on the
+          hot path; times are max over ranks.
+
+--impl reference times the reference's CPU algorithm for the same path: the float64 oracle port (oracle/oracle_c.c,
+OpenMP over all host cores) because shapely/commonroad are not installable here.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P, O_LANES, SLOTS, T = 4096, 8, 32, 50
+O = O_LANES * SLOTS
+CHECKS_PER_QUERY = P * O * T
+FLOP_PER_CHECK = 304            # rectangle x rectangle SAT, a = 8 axes, a*(4a+6)
+SAT_FLOP_EXECUTED = 160         # this kernel's full 4x4 test: 64 FMA (2 flop) + 24 min + 8 max
+CULL_FLOP_EXECUTED = 8          # centre-line axis: 2 sub, 1 add, 1 mul, 1 fma (2), 1 mul, 1 compare
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # no FP32 entry in MEASURED_PEAKS.json: derived from its sm_max_mhz
+METRIC = "primitive x obstacle x timestep collision checks/sec"
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock and throttle reasons during the timed region (NVML, ~20 ms period)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        if self.is_alive():
+            self.join(timeout=1.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            return local
+    return local
+
+
+def build_problem(nq, rank):
+    from motionplanner_b200 import workloads as W
+    lib = W.synthetic_library(P, T, seed=0)
+    scene = W.dense_traffic_scene(T, O_LANES, SLOTS, seed=1)
+    queries, origins = W.dense_traffic_queries(scene, P, nq, seed=2 + 1000 * rank)
+    return lib, scene, origins, queries
+
+
+def cpu_baseline(lib, scene, queries, budget_s=8.0):
+    """oracle port (reference semantics: float64, exact signs, early return per primitive) on all host cores"""
+    from oracle import oracle as orc
+    pb = orc.Problem(lib, scene)
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    pb.check(queries[:1], None, 0, nthreads=cores, inner_parallel=True)
+    one = time.perf_counter() - t0
+    n = int(max(1, min(len(queries) * 50, budget_s / max(one, 1e-3))))
+    qs = np.concatenate([queries] * (n // len(queries) + 1))[:n]
+    t0 = time.perf_counter()
+    _, st = pb.check(qs, None, 0, nthreads=cores, inner_parallel=True)
+    dt = time.perf_counter() - t0
+    return {"value": n * CHECKS_PER_QUERY / dt, "unit": "checks/s", "cores": cores, "kind": "port",
+            "sample": "%d C4 queries (4096x256x50 each) through oracle/oracle_c.c, OpenMP over candidates, reference "
+                      "early return per primitive; %.2f s" % (n, dt),
+            "pairs_decided_frac": st["pairs_decided"] / max(st["pairs_nominal"], 1)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU algorithm of the path (oracle port) on this box's host cores, rank 0 only"""
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build()
+    lib, scene, origins, queries = build_problem(args.ref_queries, 0)
+    pb = orc.Problem(lib, scene)
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        pb.check(queries, None, 0, nthreads=cores, inner_parallel=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, st = pb.check(queries, None, 0, nthreads=cores, inner_parallel=True)
+    dt = time.perf_counter() - t0
+    checks = args.steps * len(queries) * CHECKS_PER_QUERY
+    v = checks / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "checks/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4 dense traffic 4096 primitives x 256 obstacles x 50 timesteps per query",
+                       "queries_per_step": len(queries), "seeds": [0, 1, 2]},
+            "cpu_baseline": {"value": v, "unit": "checks/s", "cores": cores, "kind": "port",
+                             "sample": "each step = %d C4 queries through oracle/oracle_c.c (float64, exact signs, "
+                                       "reference early return), OpenMP %d threads" % (len(queries), cores)},
+            "e2e": {"value": v, "unit": "checks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "shapely/commonroad-io are not installable offline, so the reference's CPU path is timed through "
+                    "its float64 restatement (kind=port)"}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--queries", type=int, default=16, help="queries (ego poses) per step")
+    ap.add_argument("--ref-queries", type=int, default=4, help="queries per step of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the collision check has no CPU fallback (use --impl reference for "
+                         "the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from motionplanner_b200.engine import (MODE_COUNT_WORK, MODE_NO_CULL, MODE_NO_EARLY_EXIT, MODE_PLANNER,
+                                           CollisionEngine)
+    eng = CollisionEngine(local)
+    info = eng.device_info()
+    lib, scene, origins, queries = build_problem(args.queries, rank)
+    nq = len(queries)
+    eng.upload_library(lib["verts"], lib["nv"], lib["tidx"], lib["set_off"], lib["set_idx"])
+
+    def set_scene():
+        eng.set_scenes(scene["scene_step_off"], origins, scene["step_obst_off"], scene["obst"], scene["obst_nv"],
+                       scene["step_seg_begin"], scene["step_seg_end"], scene["segs"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    set_scene()
+    checks_step = nq * CHECKS_PER_QUERY
+
+    # ---- device-resident throughput (value) -------------------------------------------------------------------------
+    eng.prepare(queries, None, MODE_PLANNER)
+    eng.run_prepared(args.warmup, flush_l2=True)
+    sampler = ClockSampler(physical_gpu_index(local))
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    ms_total, ms_main, st = eng.run_prepared(args.steps, flush_l2=True)
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.result()
+    dev_s = float(ms_total.sum()) * 1e-3
+    main_ms = float(ms_main.mean())
+    collide = eng.fetch()
+
+    # warm-L2 variant (what a planner sees between expansions: library and scene stay in the 126 MB L2)
+    ms_warm, ms_main_warm, _ = eng.run_prepared(max(10, args.steps // 4), flush_l2=False)
+
+    # single-query latency on the device (B=1)
+    eng.prepare(queries[:1], None, MODE_PLANNER)
+    eng.run_prepared(3, flush_l2=False)
+    ms_one, _, _ = eng.run_prepared(50, flush_l2=False)
+
+    # instrumented launches: executed work, and the full-evaluation variant (no culling axis, no early exit)
+    eng.prepare(queries, None, MODE_PLANNER | MODE_COUNT_WORK)
+    _, _, st_cnt = eng.run_prepared(1, flush_l2=False)
+    eng.prepare(queries[:max(1, nq // 8)], None, MODE_NO_CULL | MODE_NO_EARLY_EXIT)
+    eng.run_prepared(2, flush_l2=True)
+    ms_full, ms_full_main, st_full = eng.run_prepared(5, flush_l2=True)
+    full_checks = max(1, nq // 8) * CHECKS_PER_QUERY
+
+    # ---- end to end through the public API with host buffers (e2e) ----------------------------------------------------
+    h2d = scene["obst"].nbytes + scene["obst_nv"].nbytes + scene["segs"].nbytes + scene["step_obst_off"].nbytes + \
+        2 * scene["step_seg_begin"].nbytes + queries.nbytes + origins.nbytes + scene["scene_step_off"].nbytes
+    d2h = ((P + 31) // 32) * 4 * nq + 72
+    for _ in range(args.warmup):
+        set_scene()
+        eng.query_mask(queries, None, MODE_PLANNER)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        set_scene()
+        mask, _ = eng.query_mask(queries, None, MODE_PLANNER)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    # planning-step latency: one query (B=1) against an already staged scene, host doubles in -> bitmask out
+    lat = []
+    for _ in range(60):
+        t1 = time.perf_counter()
+        eng.query_mask(queries[:1], None, MODE_PLANNER)
+        lat.append(time.perf_counter() - t1)
+    lat_p50 = float(np.median(lat[10:]))
+
+    # ---- reduce over ranks (max time), gather the result bitmasks -----------------------------------------------------
+    times = torch.tensor([dev_s, e2e_s, wall], dtype=torch.float64, device="cuda")
+    nfree = torch.tensor([float(len(collide) - int(collide.sum()))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        masks = [torch.empty(len(mask), dtype=torch.int32, device="cuda") for _ in range(world)] if rank == 0 else None
+        dist.gather(torch.from_numpy(mask.view(np.int32)).cuda(), masks, dst=0)      # only result bitmasks travel
+        dist.all_reduce(nfree)
+    dev_s, e2e_s, wall = [float(x) for x in times.cpu()]
+
+    if rank == 0:
+        value = world * args.steps * checks_step / dev_s
+        peaks = measured_peaks()
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        algo_tflops = checks_step * FLOP_PER_CHECK / (main_ms * 1e-3) / 1e12
+        exec_flop = st_cnt["cull_tests"] * CULL_FLOP_EXECUTED + st_cnt["axis_tests"] * SAT_FLOP_EXECUTED
+        exec_tflops = exec_flop / (main_ms * 1e-3) / 1e12
+        # algorithmic HBM bytes of one launch: library tile (80 B per occupancy: vertices, edge normals, circle), the
+        # scene (96 B per obstacle record), masks; shared by the Q queries of the step
+        algo_bytes = P * T * 80 + T * O * 96 + nq * ((P + 31) // 32) * 4 + nq * 64
+        full_main = float(ms_full_main.mean())
+        line = {
+            "metric": METRIC, "value": value, "unit": "checks/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+            "config": {"workload": "C4 dense traffic: 4096 primitives x 256 obstacles x 50 timesteps per query "
+                                   "(BASELINE.json configs[3])", "queries_per_step": nq,
+                       "checks_per_step": checks_step, "seeds": [0, 1, 2], "l2": "flushed before every timed step "
+                       "(256 MiB fill)", "early_exit": "warp-wide per tile", "parallelism": "replicated library, "
+                       "queries sharded per GPU, no collective on the hot path"},
+            "e2e": {"value": world * args.steps * checks_step / e2e_s, "unit": "checks/s",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "what": "CollisionEngine.set_scenes + query_mask (mpc_set_scenes + mpc_query) from host numpy "
+                            "buffers, every step"},
+            "gpu_launches": int(args.steps * 3),
+            "gpu_launches_what": "per timed step: k_fill_u32 (L2 flush, outside the event bracket), k_check, k_refine",
+            "clocks": clocks,
+            "roofline": {"bound": "fp32", "kernel": "k_check<4,4>", "achieved": algo_tflops, "peak": FP32_PEAK_TFLOPS,
+                         "unit": "TFLOP/s", "frac": algo_tflops / FP32_PEAK_TFLOPS, "traffic": None,
+                         "peak_source": "derived 148 SM x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json has no FP32 "
+                                        "figure); algorithmic = 304 flop/check (SURVEY 8d) x checks per launch",
+                         "kernel_ms": main_ms,
+                         "executed": {"cull_axis_tests": st_cnt["cull_tests"], "full_sat_tests": st_cnt["axis_tests"],
+                                      "tflops": exec_tflops, "frac": exec_tflops / FP32_PEAK_TFLOPS,
+                                      "note": "instrumented launch of the same batch: the centre-line axis decides "
+                                              "most pairs, so executed flops are far below the algorithmic count"},
+                         "full_evaluation": {"checks_per_s": full_checks / (full_main * 1e-3),
+                                             "tflops_executed": full_checks * (SAT_FLOP_EXECUTED + 0) / (full_main * 1e-3) / 1e12,
+                                             "frac": full_checks * SAT_FLOP_EXECUTED / (full_main * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
+                                             "note": "MPC_MODE_NO_CULL|NO_EARLY_EXIT: every pair runs the complete "
+                                                     "4x4 separating-axis test (160 executed flop)"},
+                         "hbm": {"algorithmic_bytes": algo_bytes, "achieved_gbs": algo_bytes / (main_ms * 1e-3) / 1e9,
+                                 "peak_gbs": hbm_peak, "frac": algo_bytes / (main_ms * 1e-3) / 1e9 / hbm_peak,
+                                 "peak_source": "measured" if peaks else "fallback"}},
+            "warm_l2": {"value": world * checks_step / (float(ms_warm.mean()) * 1e-3), "ms_per_step": float(ms_warm.mean())},
+            "latency": {"planning_step_p50_ms": 1e3 * lat_p50, "device_ms_single_query": float(np.median(ms_one)),
+                        "what": "one query (4096 candidates x 50 steps x 256 obstacles), host doubles in -> bitmask out"},
+            "refinement": {"refined_fp64": st["refined_fp64"], "exact_ties": st["exact_ties"],
+                           "near_tangent_lt_1e-9": st["near_tangent"], "parity_refined": st["parity_refined"],
+                           "tau_m": st["tau"]},
+            "result": {"free_candidates": float(nfree.item()), "candidates": world * nq * P},
+            "wall_s_timed_region": wall, "device": info["name"], "sm_count": info["sm_count"],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as orc
+            orc.build()
+            line["cpu_baseline"] = cpu_baseline(lib, scene, queries)
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
