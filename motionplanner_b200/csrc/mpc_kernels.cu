@@ -284,7 +284,7 @@ __device__ __forceinline__ float sat_obstacle(const float (&ax)[VA], const float
 }
 
 template <int VA, int VB, bool COUNT>
-__global__ void __launch_bounds__(256) k_check(const KParams p) {
+__global__ void __launch_bounds__(128, 6) k_check(const KParams p) {
     constexpr int F = ob_fields(VB);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_raw);
@@ -383,22 +383,35 @@ __global__ void __launch_bounds__(256) k_check(const KParams p) {
             const float4 *s_circ = s_ob + (F - 1) * p.cap_o;
             for (int ob = 0; ob < ocn; ob += 32) {
                 const int cnt = min(32, ocn - ob);
+                // axis 0: centre line with bounding radii.  One warp-broadcast LDS.128 per obstacle; the sign bit of
+                // e = |dc|^2 - (ra + rb + 2 tau)^2 is shifted into the hit word (bit 31-k <-> obstacle ob+k).
                 unsigned hits = 0;
                 if (!nocull) {
-#pragma unroll 4
-                    for (int k = 0; k < cnt; k++) {      // axis 0: centre line, bounding radii (warp-broadcast load)
-                        float4 c = s_circ[ob + k];
-                        float dx = c.x - acx, dy = c.y - acy, rr = c.z + arr;
-                        if (fmaf(dx, dx, dy * dy) <= rr * rr) hits |= 1u << k;
+                    if (cnt == 32) {
+#pragma unroll
+                        for (int k = 0; k < 32; k++) {
+                            float4 c = s_circ[ob + k];
+                            float dx = c.x - acx, dy = c.y - acy, rr = c.z + arr;
+                            float e = fmaf(dx, dx, fmaf(dy, dy, -(rr * rr)));
+                            hits = __funnelshift_l(__float_as_uint(e), hits, 1);
+                        }
+                    } else {
+                        for (int k = 0; k < cnt; k++) {
+                            float4 c = s_circ[ob + k];
+                            float dx = c.x - acx, dy = c.y - acy, rr = c.z + arr;
+                            float e = fmaf(dx, dx, fmaf(dy, dy, -(rr * rr)));
+                            hits = __funnelshift_l(__float_as_uint(e), hits, 1);
+                        }
+                        hits <<= 32 - cnt;
                     }
                 } else {
-                    hits = (cnt == 32) ? FULL : ((1u << cnt) - 1u);
+                    hits = ~((cnt == 32) ? 0u : (FULL >> cnt));
                 }
                 if (!active || (collide && !noexit)) hits = 0;
                 if (COUNT && active) n_cull += cnt;
                 while (hits) {
-                    int k = __ffs(hits) - 1;
-                    hits &= hits - 1;
+                    int k = __clz(hits);
+                    hits &= ~(0x80000000u >> k);
                     float sep = sat_obstacle<VA, VB>(ax, ay, anx, any_, ac, s_ob, p.cap_o, ob + k);
                     if (COUNT) n_axis++;
                     if (sep < -tau) {
