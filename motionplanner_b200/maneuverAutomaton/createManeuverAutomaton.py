@@ -28,6 +28,7 @@ def _plan(param, v_start=V_START, v_end=V_END, v_diff=V_DIFF, accelerations=ACCE
     """enumerate (v_init, acc, steer, tFinal) of every feasible primitive in reference order"""
     plan = []
     v_init = v_start
+    old = np.seterr(divide='ignore', invalid='ignore')     # tf == 0 branches divide by zero and are discarded below
     while v_init < v_end:
         for acc in accelerations:
             # stretch / shrink the primitive so that it ends on the velocity grid inside [v_start, v_end]
@@ -47,6 +48,7 @@ def _plan(param, v_start=V_START, v_end=V_END, v_diff=V_DIFF, accelerations=ACCE
                         if abs(steer) < param['s_max']:
                             plan.append((v_init, acc, steer, tf))
         v_init = v_init + v_diff
+    np.seterr(**old)
     return plan
 
 

@@ -1,0 +1,183 @@
+"""Maneuver-automaton trajectory planner with the collision checks of each expansion batched on the GPU.
+
+Drop-in for reference src/lowLevelPlannerManeuverAutomaton.py:
+    lowLevelPlannerManeuverAutomaton(scenario, planning_problem, param, space_all, ref_traj, MA, search_horizon=2)
+        -> (x, u, controller) | (None, None, None)                                                   (:19-92)
+    collision_check(node, primitive, space, param, timepoint) -> bool                                (:95-125)
+    goal_check / extract_control_inputs / transform_trajectory / expand_node / Node                  (:127-225)
+
+Search semantics kept: best-first on accumulated squared distance to the reference trajectory, stable sort of the
+queue at every iteration, lazy *use* of the collision decision when a node is popped, the "fix the first primitive
+after `search_horizon` levels" heuristic (+1000 on disagreeing queue entries), goal test on the vehicle centre.
+What changed is *when* the geometry is evaluated: when a node is expanded, all its children (one velocity bucket,
+60-195 primitives x <= 11 occupancies) are decided by a single mpc_query and each child carries its bit; popping a
+child then only applies the time guard of the reference (:99-109) and reads the bit.
+"""
+import numpy as np
+import scipy.linalg
+
+from ..checker import PrimitiveChecker, SceneSet
+from ..geometry import Point
+from ..maneuverAutomaton.Controller import FeedbackController
+
+
+class Node:
+    """search node: sequence of primitive indices, rear-axle trajectory 4 x (10 k + 1), accumulated cost"""
+
+    def __init__(self, primitives, x, cost, collides=None):
+        self.primitives = primitives
+        self.x = x
+        self.cost = cost
+        self.collides = collides          # geometry bit of the last primitive (None: not evaluated yet)
+
+
+def _rotation(phi):
+    return scipy.linalg.block_diag(np.array([[np.cos(phi), -np.sin(phi)], [np.sin(phi), np.cos(phi)]]), np.eye(2))
+
+
+def expand_node(node, primitive, ind, ref_traj, fixed, T, collides=None):
+    """child of `node` that appends primitive `ind`: trajectory, cost against the reference trajectory (:192-214)"""
+    primitives = node.primitives + [ind]
+    seg = T @ primitive.x + np.array([[node.x[0, -1]], [node.x[1, -1]], [0], [node.x[3, -1]]])
+    x = np.concatenate((node.x[:, :-1], seg), axis=1)
+    first = x.shape[1] - primitive.x.shape[1]
+    last = min(x.shape[1], ref_traj.shape[1])
+    cols = range(first, last)
+    cost = node.cost + np.sum((ref_traj[0:2, cols] - x[0:2, cols]) ** 2)
+    if len(primitives) <= len(fixed) and primitives[-1] != fixed[len(primitives) - 1]:
+        cost = cost + 1000
+    return Node(primitives, x, cost, collides)
+
+
+def _time_exceeded(ind, goals):
+    return all(ind > g['time_end'] for g in goals)
+
+
+def collision_check(node, primitive, space, param, timepoint, checker=None):
+    """check if a motion primitive is collision free (True = free) -- single-primitive form of the reference call
+    (:95-125).  `space` is the list of free-space geometries; pass `checker` to reuse staged data."""
+    ind = node.x.shape[1] - primitive.x.shape[1]
+    if _time_exceeded(ind, param['goal']):
+        return False
+    if node.collides is not None:
+        return not node.collides
+    if checker is None:
+        checker = _checker_for(param['_MA'], param['time_step'], space, timepoint)
+    x = node.x[:, ind]
+    idx = checker.index_of[id(primitive)]
+    scenes = (0,) if timepoint else (0, 1)
+    return not bool(checker.list_collides(x[0], x[1], x[3], ind, param['steps'], [idx], scenes)[0])
+
+
+_CACHE = {}
+
+
+def _checker_for(MA, time_step, space, timepoint, backend=None):
+    """stage automaton + free space once per (automaton, space list) pair"""
+    key = (id(MA), float(time_step), id(space), bool(timepoint), id(backend))
+    hit = _CACHE.get('k')
+    if hit is not None and hit[0] == key and hit[1] is space:
+        return hit[2]
+    chk = PrimitiveChecker(MA, time_step, backend)
+    scenes = SceneSet()
+    if timepoint:
+        scenes.add_scene_from_spaces(space)
+    else:
+        # interval occupancies: the reference intersects consecutive free spaces (:27-30); a convex set lies in
+        # A n B iff it lies in A and in B, so the occupancy is tested against both steps instead
+        scenes.add_scene_from_spaces(space[:-1])
+        scenes.add_scene_from_spaces(space[1:])
+    chk.set_scenes(scenes)
+    _CACHE['k'] = (key, space, chk)
+    return chk
+
+
+def goal_check(node, primitive, param):
+    """first step of the last primitive whose vehicle centre lies in a goal set inside its time window (:127-142)"""
+    ind = node.x.shape[1] - primitive.x.shape[1]
+    for i in range(ind, node.x.shape[1]):
+        for goal in param['goal']:
+            if goal['time_start'] <= i <= goal['time_end']:
+                p = Point(node.x[0, i] + np.cos(node.x[3, i]) * param['b'],
+                          node.x[1, i] + np.sin(node.x[3, i]) * param['b'])
+                if goal['space'] is None or goal['space'].contains(p):
+                    return True, i
+    return False, None
+
+
+def extract_control_inputs(node, primitives):
+    """piecewise-constant input sequence of the node's primitives (:168-181)"""
+    parts = [np.expand_dims(primitives[i].u, axis=1) @ np.ones((1, primitives[i].x.shape[1] - 1))
+             for i in node.primitives]
+    return np.concatenate(parts, axis=1) if parts else []
+
+
+def transform_trajectory(x, param):
+    """rear axle -> vehicle centre, in place (:183-190)"""
+    for i in range(x.shape[1]):
+        x[0, i] = x[0, i] + np.cos(x[3, i]) * param['b']
+        x[1, i] = x[1, i] + np.sin(x[3, i]) * param['b']
+    return x
+
+
+def _children(checker, node, MA, bucket, ref_traj, fixed, param, scenes):
+    """expand `node` by every primitive of velocity bucket `bucket`; one device query decides all of them"""
+    ind = node.x.shape[1] - 1
+    cand = MA.vel_dic[bucket]
+    if not cand:
+        return []
+    if _time_exceeded(ind, param['goal']):
+        bits = np.ones(len(cand), bool)           # the reference rejects these before looking at geometry (:99-109)
+    else:
+        bits = checker.bucket_collides(node.x[0, -1], node.x[1, -1], node.x[3, -1], ind, param['steps'], bucket, scenes)
+    T = _rotation(node.x[3, -1])
+    return [expand_node(node, MA.primitives[i], i, ref_traj, fixed, T, bool(b)) for i, b in zip(cand, bits)]
+
+
+def lowLevelPlannerManeuverAutomaton(scenario, planning_problem, param, space_all, ref_traj, MA, search_horizon=2,
+                                     backend=None):
+    """plan a concrete trajectory for the given high-level plan using a maneuver automaton"""
+    timepoint = MA.is_timepoint()
+    checker = _checker_for(MA, param['time_step'], space_all, timepoint, backend)
+    scenes = (0,) if timepoint else (0, 1)
+    param['_MA'] = MA
+
+    # initial state, shifted from the vehicle centre to the rear axle (:33-36)
+    x = np.expand_dims(np.array([param['x0'][0], param['x0'][1], param['v_init'], param['orientation']]), 1)
+    x[0, 0] = x[0, 0] - np.cos(x[3, 0]) * param['b']
+    x[1, 0] = x[1, 0] - np.sin(x[3, 0]) * param['b']
+
+    node = Node([], x, 0)
+    cnt, fixed = 0, []
+    queue = _children(checker, node, MA, int(MA._bucket(param['v_init'])), ref_traj, fixed, param, scenes)
+
+    while len(queue) > 0:
+        queue.sort(key=lambda n: n.cost)
+        node = queue.pop(0)
+        primitive = MA.primitives[node.primitives[-1]]
+
+        if collision_check(node, primitive, space_all, param, timepoint, checker):
+
+            # fix the first not yet fixed primitive once the search is `search_horizon` levels ahead of it (:64-69)
+            if len(node.primitives) == cnt + search_horizon:
+                for other in queue:
+                    if cnt < len(other.primitives) and other.primitives[cnt] != node.primitives[cnt]:
+                        other.cost = other.cost + 1000
+                fixed.append(node.primitives[cnt])
+                cnt = cnt + 1
+
+            res, ind = goal_check(node, primitive, param)
+            if res:
+                if timepoint:
+                    u = extract_control_inputs(node, MA.primitives)
+                    t = param['time_step'] * np.arange(0, x.shape[1] + 1)
+                    K = [np.zeros([u.shape[0], x.shape[0]]) for _ in range(u.shape[1])]
+                    controller = FeedbackController(x, u, t, K)
+                    return transform_trajectory(node.x[:, :ind + 1], param), u[:, :ind], controller
+                raise NotImplementedError("interval-occupancy automata need the AROC controllers "
+                                          "(reference loadAROCcontroller, out of scope: SURVEY.md section 2 #8)")
+
+            queue.extend(_children(checker, node, MA, int(MA._bucket(primitive.x[2, -1])), ref_traj, fixed, param,
+                                   scenes))
+
+    return None, None, None
