@@ -1,0 +1,140 @@
+"""The primitive-selection step (reference src/lowLevelPlannerManeuverAutomaton.py:19-92) behind its unchanged
+signature: corridor given as one free-space polygon per time step (with a hole where an obstacle was subtracted),
+reference trajectory, the regenerated automaton.  CPU: the oracle stands in for the engine; GPU: the product engine
+must produce the identical plan, decision by decision."""
+import numpy as np
+import pytest
+
+from helpers import OracleBackend
+from motionplanner_b200.geometry import Polygon
+from motionplanner_b200.maneuverAutomaton.createManeuverAutomaton import load_maneuver_automaton
+from motionplanner_b200.src import lowLevelPlannerManeuverAutomaton as LL
+from motionplanner_b200.vehicle.vehicleParameter import vehicleParameter
+from oracle import exact as ex
+
+
+@pytest.fixture(scope="module")
+def MA():
+    return load_maneuver_automaton()
+
+
+def corridor_problem(v=10.0, steps=40, blocked=True):
+    param = vehicleParameter()
+    param.update({'time_step': 0.1, 'steps': steps, 'x0': np.array([0.0, 0.0]), 'v_init': v, 'orientation': 0.0,
+                  'goal': [{'time_start': steps - 10, 'time_end': steps, 'space': None}]})
+    shell = [(-10.0, -1.75), (200.0, -1.75), (200.0, 5.25), (-10.0, 5.25)]          # two lanes
+    space = []
+    for t in range(steps + 1):
+        if blocked and 8 <= t <= 30:
+            x0 = 22.0 + 2.0 * 0.1 * t                                                # slow car ahead in the ego lane
+            hole = [(x0, -1.0), (x0, 1.0), (x0 + 4.5, 1.0), (x0 + 4.5, -1.0)]
+            space.append(Polygon(shell, [hole]))
+        else:
+            space.append(Polygon(shell))
+    t = np.arange(steps + 1) * 0.1
+    ref = np.stack([v * t, np.zeros_like(t), np.full_like(t, v), np.zeros_like(t)])
+    if blocked:                                                                       # reference line moves to lane 2
+        ref[1] = np.clip((t - 0.5) * 3.5 / 1.0, 0.0, 3.5)
+    return param, space, ref
+
+
+def plan_is_inside(x_centre, space, param):
+    """every ego rectangle of the returned centre-frame trajectory lies in the free space of its step (exact)"""
+    for i in range(x_centre.shape[1]):
+        car = ex.rectangle_vertices(param['length'], param['width'], x_centre[0, i], x_centre[1, i],
+                                    np.cos(x_centre[3, i]), np.sin(x_centre[3, i]))
+        rings = [list(space[i].exterior.coords)] + [list(h.coords) for h in space[i].interiors]
+        if not ex.region_contains_convex(rings, car):
+            return False
+    return True
+
+
+def run(MA, backend, **kw):
+    param, space, ref = corridor_problem(**kw)
+    LL._CACHE.clear()
+    x, u, ctrl = LL.lowLevelPlannerManeuverAutomaton(None, None, param, space, ref, MA, backend=backend)
+    return x, u, ctrl, param, space
+
+
+def test_planner_cpu_free_corridor(MA):
+    x, u, ctrl, param, space = run(MA, OracleBackend(), blocked=False)
+    assert x is not None and x.shape[0] == 4 and u.shape == (2, x.shape[1] - 1)
+    assert param['goal'][0]['time_start'] <= x.shape[1] - 1 <= param['goal'][0]['time_end']
+    assert np.abs(x[1]).max() < 0.5                       # stays on the reference line
+    assert plan_is_inside(x, space, param)
+    # the reference hands the *initial state* to FeedbackController (src/lowLevelPlannerManeuverAutomaton.py:77-78,
+    # `x` is never reassigned); kept as is
+    assert ctrl.x_ref.shape == (4, 1) and ctrl.u_ref.shape[0] == 2 and len(ctrl.K) == ctrl.u_ref.shape[1]
+
+
+def test_planner_cpu_lane_change_around_hole(MA):
+    be = OracleBackend()
+    x, u, ctrl, param, space = run(MA, be, blocked=True)
+    assert x is not None
+    assert x[1].max() > 2.0                               # it moved to the second lane
+    assert plan_is_inside(x, space, param)
+    assert len(be.log) >= 3                               # one batched query per expansion, not one per child
+
+
+def test_collision_check_single_call_matches_batched(MA):
+    """module-level collision_check(node, primitive, space, param, timepoint): same decision as the batched bit"""
+    param, space, ref = corridor_problem(blocked=True)
+    be = OracleBackend()
+    LL._CACHE.clear()
+    chk = LL._checker_for(MA, 0.1, space, True, be)
+    param['_MA'] = MA
+    x = np.array([[0.0 - 1.15], [0.0], [10.0], [0.0]])
+    root = LL.Node([], x, 0)
+    bucket = int(MA._bucket(10.0))
+    kids = LL._children(chk, root, MA, bucket, ref, [], param, (0,))
+    for k in kids[::17]:
+        prim = MA.primitives[k.primitives[-1]]
+        lazy = LL.Node(k.primitives, k.x, k.cost, None)
+        assert LL.collision_check(lazy, prim, space, param, True, chk) == (not k.collides)
+    # time guard (reference :99-109): a node whose parent index lies beyond every goal's time_end is rejected
+    late = LL.Node([kids[0].primitives[-1]], np.zeros((4, 61)), 0.0, False)
+    assert LL.collision_check(late, MA.primitives[kids[0].primitives[-1]], space, param, True, chk) is False
+
+
+@pytest.mark.gpu
+def test_planner_gpu_identical_plan(MA):
+    from motionplanner_b200.engine import CollisionEngine
+    for blocked in (False, True):
+        cpu = OracleBackend()
+        x0, u0, _, _, _ = run(MA, cpu, blocked=blocked)
+        eng = CollisionEngine(0)
+        x1, u1, _, param, space = run(MA, eng, blocked=blocked)
+        eng.close()
+        assert x0 is not None and x1 is not None
+        assert np.array_equal(x0, x1) and np.array_equal(u0, u1)
+        assert plan_is_inside(x1, space, param)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# stand-alone planner (reference src/maneuverAutomatonPlannerStandalone.py) on a bundled scenario with a goal region
+# ---------------------------------------------------------------------------------------------------------------------
+import os  # noqa: E402
+
+REF_SCENARIOS = '/root/reference/scenarios'
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SCENARIOS), reason="reference scenarios not mounted (build container only)")
+def test_standalone_planner_cpu_on_zam_zip(MA):
+    """BASELINE.json configs[0] scenario (ZAM_Zip-1_19_T-1, goal = lanelet 24 in steps 84..85): the stand-alone planner
+    finds a plan with one batched query per expansion and the plan passes the trajectory validator"""
+    from motionplanner_b200.auxiliary import collisionChecker as CC
+    from motionplanner_b200.crlite import CommonRoadFileReader
+    from motionplanner_b200.src.maneuverAutomatonPlannerStandalone import (get_goal_set,
+                                                                           maneuverAutomatonPlannerStandalone)
+    scenario, pps = CommonRoadFileReader(os.path.join(REF_SCENARIOS, 'ZAM_Zip-1_19_T-1.xml')).open()
+    goals = get_goal_set(scenario, list(pps.planning_problem_dict.values())[0])
+    assert len(goals) == 1 and goals[0]['lane'] == 24 and (goals[0]['time_start'], goals[0]['time_end']) == (84, 85)
+    param = vehicleParameter()
+    be = OracleBackend()
+    x, u, ctrl = maneuverAutomatonPlannerStandalone(scenario, pps, param, MA, backend=be, max_nodes=20000)
+    assert param['steps'] == 86 and param['timepoint'] is True
+    assert x is not None and x.shape == (4, 85) and u.shape == (2, 84)
+    assert 20 < len(be.log) < 200                       # batched: one query per expansion
+    flags, _ = CC.collision_flags(scenario, x, param, engine=OracleBackend())
+    assert not flags.any()
+    assert goals[0]['space'].contains(LL.Point(x[0, -1], x[1, -1]))
