@@ -184,6 +184,9 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # NCCL and friends may print to stdout: keep fd 1 for the single JSON line, send everything else to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -337,7 +340,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline(lib, scene, queries)
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     eng.close()
     if world > 1:
         dist.destroy_process_group()

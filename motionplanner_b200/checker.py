@@ -216,6 +216,8 @@ class PrimitiveChecker:
         lay = self.layout
         self.backend.upload_library(lay['verts'], lay['nv'], lay['tidx'], lay['set_off'], lay['set_idx'])
         self.index_of = {id(p): i for i, p in enumerate(MA.primitives)}
+        self._set_len = np.diff(lay['set_off'])
+        self._qbuf = {}
         self.nscenes = 0
         self.mode = MODE_PLANNER
         self.stats = dict(queries=0, candidates=0, refined_fp64=0, near_tangent=0, exact_ties=0, pairs_nominal=0)
@@ -235,15 +237,30 @@ class PrimitiveChecker:
     def bucket_collides(self, x, y, phi, t0, step_limit, bucket, scenes=(0,)):
         """collision bits (True = collides) of every primitive of velocity bucket `bucket` appended at pose
         (x, y, phi) and time index t0; with several scenes a candidate collides if it does in any of them"""
-        cnt = int(self.layout['set_off'][bucket + 1] - self.layout['set_off'][bucket])
-        q = make_queries(len(scenes))
+        cnt = int(self._set_len[bucket])
+        ns = len(scenes)
+        q = self._qbuf.get(ns)
+        if q is None:
+            q = self._qbuf[ns] = make_queries(ns)
+            q['cand_off'] = 0
         q['x'], q['y'], q['c'], q['s'] = x, y, np.cos(phi), np.sin(phi)
-        q['t0'], q['step_limit'] = t0, step_limit
-        q['cand_set'], q['cand_off'], q['cand_cnt'] = bucket, 0, cnt
-        q['scene'] = list(scenes)
+        q['t0'], q['step_limit'], q['cand_set'], q['cand_cnt'] = t0, step_limit, bucket, cnt
+        q['scene'] = scenes
+        if hasattr(self.backend, 'query_fast'):
+            mask, st = self.backend.query_fast(q, self.mode, want_stats=True)
+            nw = (cnt + 31) // 32
+            bits = np.unpackbits(mask.view(np.uint8).reshape(ns, nw * 4), axis=1, bitorder='little')[:, :cnt]
+            s = self.stats
+            s['queries'] += 1
+            s['candidates'] += cnt * ns
+            s['refined_fp64'] += st.refined_fp64
+            s['near_tangent'] += st.near_tangent
+            s['exact_ties'] += st.exact_ties
+            s['pairs_nominal'] += st.pairs_nominal
+            return bits.any(axis=0) if ns > 1 else bits[0].astype(bool)
         bits, st = self.backend.query(q, None, self.mode)
-        self._account(st, cnt * len(scenes))
-        return bits.reshape(len(scenes), cnt).any(axis=0)
+        self._account(st, cnt * ns)
+        return bits.reshape(ns, cnt).any(axis=0)
 
     def list_collides(self, x, y, phi, t0, step_limit, prim_indices, scenes=(0,)):
         """same for an explicit list of primitive indices"""

@@ -28,6 +28,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -67,7 +68,7 @@ struct KParams {
     const int *ob_nv;
     int ob_stride, ob_vmax;
     const int *step_obst_off, *step_seg_begin, *step_seg_end;
-    const float4 *sg_f;
+    const float4 *sg_f, *sg_box;
     const double *sg_64;
     int sg_stride;
     const float *maxabs_scene;
@@ -214,28 +215,47 @@ __global__ void k_stage_obst(int nobst, double *__restrict__ ob64, const int *__
         ob_f[(size_t)f * stride + o] = make_float4(out[4 * f], out[4 * f + 1], out[4 * f + 2], out[4 * f + 3]);
 }
 
-__global__ void k_stage_segs(int nseg, const double *__restrict__ sg64, const int *__restrict__ seg_scene,
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// one thread per segment slot (slots are laid out in 32-aligned, spatially sorted ranges by the host); a warp = one
+// block of 32 slots and also reduces the block's bounding box (of the float32 data the main kernel will see)
+__global__ void k_stage_segs(int nslots, const double *__restrict__ sg64, const int *__restrict__ seg_scene,
                              const double *__restrict__ origins, float4 *__restrict__ sg_f, int stride,
-                             float *maxabs) {
+                             float4 *__restrict__ sg_box, float *maxabs) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nseg) return;
-    int sc = seg_scene[s];
-    double ax = sg64[4 * s], ay = sg64[4 * s + 1], bx = sg64[4 * s + 2], by = sg64[4 * s + 3];
-    double ex = bx - ax, ey = by - ay;
-    double len = sqrt(ex * ex + ey * ey);
-    if (sc < 0 || !(len > 0.0)) {      // unused or degenerate: far away, never near, never straddling
-        sg_f[s] = make_float4(FAR, FAR, FAR, FAR);
-        sg_f[(size_t)stride + s] = make_float4(0.f, 0.f, BIG, -1.f);
-        return;
+    bool valid = false;
+    float4 rec = make_float4(FAR, FAR, FAR, FAR), line = make_float4(0.f, 0.f, BIG, -1.f);
+    if (s < nslots) {
+        int sc = seg_scene[s];
+        double ax = sg64[4 * s], ay = sg64[4 * s + 1], bx = sg64[4 * s + 2], by = sg64[4 * s + 3];
+        double ex = bx - ax, ey = by - ay;
+        double len = sqrt(ex * ex + ey * ey);
+        if (sc >= 0 && len > 0.0) {       // else: padding or degenerate: far away, never near, never straddling
+            double ox = origins[2 * sc], oy = origins[2 * sc + 1];
+            double lax = ax - ox, lay = ay - oy, lbx = bx - ox, lby = by - oy;
+            double nx = ey / len, ny = -ex / len;      // right-hand normal of a->b
+            rec = make_float4((float)lax, (float)lay, (float)lbx, (float)lby);
+            line = make_float4((float)nx, (float)ny, (float)(nx * lax + ny * lay), __double2float_ru(0.5 * len * (1.0 + 1e-6)));
+            double m = fmax(fmax(fabs(lax), fabs(lay)), fmax(fabs(lbx), fabs(lby)));
+            atomic_max_pos_float(maxabs, __double2float_ru(m));
+            valid = true;
+        }
+        sg_f[s] = rec;
+        sg_f[(size_t)stride + s] = line;
     }
-    double ox = origins[2 * sc], oy = origins[2 * sc + 1];
-    double lax = ax - ox, lay = ay - oy, lbx = bx - ox, lby = by - oy;
-    double nx = ey / len, ny = -ex / len;      // right-hand normal of a->b
-    sg_f[s] = make_float4((float)lax, (float)lay, (float)lbx, (float)lby);
-    sg_f[(size_t)stride + s] = make_float4((float)nx, (float)ny, (float)(nx * lax + ny * lay),
-                                           __double2float_ru(0.5 * len * (1.0 + 1e-6)));
-    double m = fmax(fmax(fabs(lax), fabs(lay)), fmax(fabs(lbx), fabs(lby)));
-    atomic_max_pos_float(maxabs, __double2float_ru(m));
+    float x0 = valid ? fminf(rec.x, rec.z) : BIG, x1 = valid ? fmaxf(rec.x, rec.z) : -BIG;
+    float y0 = valid ? fminf(rec.y, rec.w) : BIG, y1 = valid ? fmaxf(rec.y, rec.w) : -BIG;
+    x0 = warp_min(x0); y0 = warp_min(y0); x1 = warp_max(x1); y1 = warp_max(y1);
+    if ((threadIdx.x & 31) == 0 && s < nslots) sg_box[s >> 5] = make_float4(x0, y0, x1, y1);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -425,51 +445,96 @@ __global__ void __launch_bounds__(128, 6) k_check(const KParams p) {
             }
 
             // ---- boundary segments of the free space at this time step -----------------------------------------
-            for (int sb = 0; sb < scn; sb += 32) {
-                const int cnt = min(32, scn - sb);
-                unsigned hits = 0;
+            if (scn) {
+                // bounding box of the warp's 32 polygon centres and their largest radius: decides which 32-blocks of
+                // the (spatially sorted) segment range can matter for anyone in the warp
+                const bool blockcull = !nocull && nseg > 32;      // a single block cannot be skipped: no box work
+                float wx0 = 0.f, wx1 = 0.f, wy0 = 0.f, wy1 = 0.f, wr = 0.f;
+                if (blockcull) {
+                    wx0 = warp_min(active ? acx : BIG); wx1 = warp_max(active ? acx : -BIG);
+                    wy0 = warp_min(active ? acy : BIG); wy1 = warp_max(active ? acy : -BIG);
+                    wr = warp_max(active ? arr : 0.f);
+                }
+                const float4 *boxes = p.sg_box + ((g0 + sc0) >> 5);
+                // the even-odd ray may run along +x, -x, +y or -y; take the direction whose ray corridor meets the
+                // fewest blocks of the whole range (a road aligned with the ray would otherwise keep every block alive)
+                int dir = 0;
+                if (blockcull) {
+                    const float4 *all = p.sg_box + (g0 >> 5);
+                    const int nblk = (nseg + 31) >> 5;
+                    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+                    for (int b = lane; b < ((nblk + 31) & ~31); b += 32) {
+                        float4 bb = (b < nblk) ? __ldg(all + b) : make_float4(BIG, BIG, -BIG, -BIG);
+                        const bool iny = bb.w >= wy0 && bb.y <= wy1, inx = bb.z >= wx0 && bb.x <= wx1;
+                        c0 += __popc(__ballot_sync(FULL, iny && bb.z >= wx0));      // +x
+                        c1 += __popc(__ballot_sync(FULL, iny && bb.x <= wx1));      // -x
+                        c2 += __popc(__ballot_sync(FULL, inx && bb.w >= wy0));      // +y
+                        c3 += __popc(__ballot_sync(FULL, inx && bb.y <= wy1));      // -y
+                    }
+                    int best = c0;
+                    if (c1 < best) { best = c1; dir = 1; }
+                    if (c2 < best) { best = c2; dir = 2; }
+                    if (c3 < best) { best = c3; dir = 3; }
+                }
+                const bool ray_y = dir >= 2, flip = (dir == 1) || (dir == 2);
+                const float pc = ray_y ? acx : acy;          // coordinate the ray keeps constant
+                for (int sb = 0; sb < scn; sb += 32) {
+                    const int cnt = min(32, scn - sb);
+                    if (blockcull) {
+                        const float4 bb = __ldg(boxes + (sb >> 5));
+                        // a segment can meet a polygon only if the boxes overlap; it can be crossed by the ray of a
+                        // centre only if it reaches that centre's constant coordinate and is not entirely behind it
+                        const bool sat_rel = bb.x <= wx1 + wr && bb.z >= wx0 - wr && bb.y <= wy1 + wr && bb.w >= wy0 - wr;
+                        const bool iny = bb.w >= wy0 && bb.y <= wy1, inx = bb.z >= wx0 && bb.x <= wx1;
+                        const bool par_rel = dir == 0 ? (iny && bb.z >= wx0) : dir == 1 ? (iny && bb.x <= wx1)
+                                           : dir == 2 ? (inx && bb.w >= wy0) : (inx && bb.y <= wy1);
+                        if (!sat_rel && !par_rel) continue;
+                    }
+                    unsigned hits = 0;
 #pragma unroll 2
-                for (int k = 0; k < cnt; k++) {
-                    float4 sa = s_sg[sb + k], sl = s_sg[p.cap_s + sb + k];
-                    float dl = fmaf(sl.x, acx, fmaf(sl.y, acy, -sl.z));       // centre to the segment's line
-                    // even-odd crossing parity of the +x ray from the polygon centre
-                    bool ua = sa.y > acy, ub = sa.w > acy;
-                    if (ua != ub) {
-                        par ^= ub ? (dl < 0.f) : (dl > 0.f);
-                        punc |= fabsf(dl) <= tau;
+                    for (int k = 0; k < cnt; k++) {
+                        float4 sa = s_sg[sb + k], sl = s_sg[p.cap_s + sb + k];
+                        float dl = fmaf(sl.x, acx, fmaf(sl.y, acy, -sl.z));       // centre to the segment's line
+                        // even-odd crossing parity of the ray from the polygon centre.  The two comparisons are exact
+                        // on the float32 data and consistent between segments that share a vertex; the side test is
+                        // trusted only outside the error band
+                        const float ea = ray_y ? sa.x : sa.y, eb = ray_y ? sa.z : sa.w;
+                        bool ua = ea > pc, ub = eb > pc;
+                        if (ua != ub) {
+                            par ^= (ub != flip) ? (dl < 0.f) : (dl > 0.f);
+                            punc |= fabsf(dl) <= tau;
+                        }
+                        float tt = fmaf(-sl.y, acx - 0.5f * (sa.x + sa.z), sl.x * (acy - 0.5f * (sa.y + sa.w)));
+                        bool near = nocull ? (sl.w >= 0.f) : ((fabsf(dl) <= arr) & (fabsf(tt) <= sl.w + arr));
+                        if (near) hits |= 1u << k;
                     }
-                    punc |= (fabsf(sa.y - acy) <= tau) | (fabsf(sa.w - acy) <= tau);
-                    float tt = fmaf(-sl.y, acx - 0.5f * (sa.x + sa.z), sl.x * (acy - 0.5f * (sa.y + sa.w)));
-                    bool near = nocull ? (sl.w >= 0.f) : ((fabsf(dl) <= arr) & (fabsf(tt) <= sl.w + arr));
-                    if (near) hits |= 1u << k;
-                }
-                if (!active || (collide && !noexit)) hits = 0;
-                if (COUNT && active) n_cull += cnt;
-                while (hits) {
-                    int k = __ffs(hits) - 1;
-                    hits &= hits - 1;
-                    float4 sa = s_sg[sb + k], sl = s_sg[p.cap_s + sb + k];
-                    float sep = -BIG, mn = BIG, mx = -BIG;
+                    if (!active || (collide && !noexit)) hits = 0;
+                    if (COUNT && active) n_cull += cnt;
+                    while (hits) {
+                        int k = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        float4 sa = s_sg[sb + k], sl = s_sg[p.cap_s + sb + k];
+                        float sep = -BIG, mn = BIG, mx = -BIG;
 #pragma unroll
-                    for (int e = 0; e < VA; e++) {
-                        float d0 = fmaf(anx[e], sa.x, fmaf(any_[e], sa.y, -ac[e]));
-                        float d1 = fmaf(anx[e], sa.z, fmaf(any_[e], sa.w, -ac[e]));
-                        sep = fmaxf(sep, fminf(d0, d1));
-                        float d = fmaf(sl.x, ax[e], fmaf(sl.y, ay[e], -sl.z));
-                        mn = fminf(mn, d);
-                        mx = fmaxf(mx, d);
+                        for (int e = 0; e < VA; e++) {
+                            float d0 = fmaf(anx[e], sa.x, fmaf(any_[e], sa.y, -ac[e]));
+                            float d1 = fmaf(anx[e], sa.z, fmaf(any_[e], sa.w, -ac[e]));
+                            sep = fmaxf(sep, fminf(d0, d1));
+                            float d = fmaf(sl.x, ax[e], fmaf(sl.y, ay[e], -sl.z));
+                            mn = fminf(mn, d);
+                            mx = fmaxf(mx, d);
+                        }
+                        sep = fmaxf(sep, fmaxf(mn, -mx));
+                        if (COUNT) n_axis++;
+                        if (sep < -tau) {
+                            collide = true;
+                            if (!noexit) hits = 0;
+                        } else if (!(sep > tau)) {
+                            push_work(p, q, ci, j, KIND_SEG, g0 + sc0 + sb + k);
+                        }
                     }
-                    sep = fmaxf(sep, fmaxf(mn, -mx));
-                    if (COUNT) n_axis++;
-                    if (sep < -tau) {
-                        collide = true;
-                        if (!noexit) hits = 0;
-                    } else if (!(sep > tau)) {
-                        push_work(p, q, ci, j, KIND_SEG, g0 + sc0 + sb + k);
-                    }
+                    if (!noexit && __all_sync(FULL, collide || !active)) break;
                 }
-                // no warp-wide exit here: lanes that are still free need the parity of every segment
-                if (!noexit && __all_sync(FULL, collide || !active)) break;
             }
 
             // ---- fold this phase into the group state ----------------------------------------------------------
@@ -510,60 +575,83 @@ __global__ void __launch_bounds__(128, 6) k_check(const KParams p) {
 __global__ void __launch_bounds__(128) k_refine(const KParams p) {
     const unsigned n = min(p.cnt->wl_count, (unsigned)p.wl_cap);
     unsigned refined = 0, ties = 0, near_t = 0, par_ref = 0;
-    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
-        const int4 e = p.wl[idx];
-        const int q = e.x, ci = e.y, j = e.z & 0xffff, kind = e.z >> 16, obj = e.w;
-        const QDev *Q = p.q + q;
-        const int pj = p.cand[Q->cand_base + ci] * p.J + j;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned nthreads = gridDim.x * blockDim.x;
+    for (unsigned base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += nthreads) {   // warp-uniform
+        const unsigned idx = base + lane;
+        const bool have = idx < n;
+        int q = 0, ci = 0, kind = -1;
+        const QDev *Q = p.q;
         Poly64 A;
-        A.n = p.lib_nv[pj];
-        const double *lv = p.lib_v64 + (size_t)pj * p.lib_vmax * 2;
-        // shapely affine_transform(o['space'], [cos, -sin, sin, cos, x, y]): xp = a*x + b*y + xoff, left to right
-        const double a = Q->c, b = -Q->s, d = Q->s, ee = Q->c;
-        for (int k = 0; k < A.n; k++) {
-            A.x[k] = __dadd_rn(__dadd_rn(__dmul_rn(a, lv[2 * k]), __dmul_rn(b, lv[2 * k + 1])), Q->x);
-            A.y[k] = __dadd_rn(__dadd_rn(__dmul_rn(d, lv[2 * k]), __dmul_rn(ee, lv[2 * k + 1])), Q->y);
-        }
+        A.n = 0;
         bool collide = false;
-        if (kind == KIND_OBST) {
-            Poly64 Bp;
-            Bp.n = p.ob_nv[obj];
-            const double *bv = p.ob_v64 + (size_t)obj * p.ob_vmax * 2;
-            for (int k = 0; k < Bp.n; k++) { Bp.x[k] = bv[2 * k]; Bp.y[k] = bv[2 * k + 1]; }
-            collide = convex_collide(A, Bp, p.mode & MPC_MODE_VALIDATOR, ties);
-            if (fabs(approx_sep(A, Bp)) < 1e-9) near_t++;
-            refined++;
-        } else if (kind == KIND_SEG) {
-            const double *sg = p.sg_64 + 4 * (size_t)obj;
-            collide = segment_meets_interior(A, sg[0], sg[1], sg[2], sg[3], ties);
-            refined++;
-        } else {
-            double cx = 0.0, cy = 0.0;
-            for (int k = 0; k < A.n; k++) { cx += A.x[k]; cy += A.y[k]; }
-            cx /= A.n; cy /= A.n;
-            const int step = Q->step0 + Q->t0 + p.slot_t[j];
-            const int g0 = p.step_seg_begin[step], g1 = p.step_seg_end[step];
+        double cx = 0.0, cy = 0.0;
+        int g0 = 0, g1 = 0;
+        if (have) {
+            const int4 e = p.wl[idx];
+            q = e.x; ci = e.y; kind = e.z >> 16;
+            const int j = e.z & 0xffff, obj = e.w;
+            Q = p.q + q;
+            const int pj = p.cand[Q->cand_base + ci] * p.J + j;
+            A.n = p.lib_nv[pj];
+            const double *lv = p.lib_v64 + (size_t)pj * p.lib_vmax * 2;
+            // shapely affine_transform(o['space'], [cos, -sin, sin, cos, x, y]): xp = a*x + b*y + xoff, left to right
+            const double a = Q->c, b = -Q->s, d = Q->s, ee = Q->c;
+            for (int k = 0; k < A.n; k++) {
+                A.x[k] = __dadd_rn(__dadd_rn(__dmul_rn(a, lv[2 * k]), __dmul_rn(b, lv[2 * k + 1])), Q->x);
+                A.y[k] = __dadd_rn(__dadd_rn(__dmul_rn(d, lv[2 * k]), __dmul_rn(ee, lv[2 * k + 1])), Q->y);
+            }
+            if (kind == KIND_OBST) {
+                Poly64 Bp;
+                Bp.n = p.ob_nv[obj];
+                const double *bv = p.ob_v64 + (size_t)obj * p.ob_vmax * 2;
+                for (int k = 0; k < Bp.n; k++) { Bp.x[k] = bv[2 * k]; Bp.y[k] = bv[2 * k + 1]; }
+                collide = convex_collide(A, Bp, p.mode & MPC_MODE_VALIDATOR, ties);
+                if (fabs(approx_sep(A, Bp)) < 1e-9) near_t++;
+                refined++;
+            } else if (kind == KIND_SEG) {
+                const double *sg = p.sg_64 + 4 * (size_t)obj;
+                collide = segment_meets_interior(A, sg[0], sg[1], sg[2], sg[3], ties);
+                refined++;
+            } else {
+                for (int k = 0; k < A.n; k++) { cx += A.x[k]; cy += A.y[k]; }
+                cx /= A.n; cy /= A.n;
+                const int step = Q->step0 + Q->t0 + p.slot_t[j];
+                g0 = p.step_seg_begin[step];
+                g1 = p.step_seg_end[step];
+                par_ref++;
+            }
+        }
+        // inside/outside of an occupancy centre, exact: the warp shares the segment loop of each such item
+        unsigned todo = __ballot_sync(FULL, have && kind == KIND_PARITY);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const double bx = __shfl_sync(FULL, cx, src), by = __shfl_sync(FULL, cy, src);
+            const int b0 = __shfl_sync(FULL, g0, src), b1 = __shfl_sync(FULL, g1, src);
             bool inside = false, on_edge = false;
-            for (int g = g0; g < g1; g++) {
+            for (int g = b0 + (int)lane; g < b1; g += 32) {
                 const double *sg = p.sg_64 + 4 * (size_t)g;
                 const double sax = sg[0], say = sg[1], sbx = sg[2], sby = sg[3];
-                int o = orient2d(sax, say, sbx, sby, cx, cy, ties);
-                if (o == 0 && fmin(sax, sbx) <= cx && cx <= fmax(sax, sbx) && fmin(say, sby) <= cy && cy <= fmax(say, sby))
+                if (sax == sbx && say == sby) continue;
+                int o = orient2d(sax, say, sbx, sby, bx, by, ties);
+                if (o == 0 && fmin(sax, sbx) <= bx && bx <= fmax(sax, sbx) && fmin(say, sby) <= by && by <= fmax(say, sby))
                     on_edge = true;
-                if ((say > cy) != (sby > cy)) {
+                if ((say > by) != (sby > by)) {
                     if ((sby > say && o > 0) || (sby < say && o < 0)) inside = !inside;
                 }
             }
-            collide = on_edge || !inside;
-            par_ref++;
+            const unsigned odd = __popc(__ballot_sync(FULL, inside)) & 1u;
+            const bool edge = __any_sync(FULL, on_edge);
+            if ((int)lane == src) collide = edge || !odd;
         }
-        if (collide) atomicOr(p.mask + Q->mask_off + (ci >> 5), 1u << (ci & 31));
+        if (have && collide) atomicOr(p.mask + Q->mask_off + (ci >> 5), 1u << (ci & 31));
     }
     refined = __reduce_add_sync(FULL, refined);
     ties = __reduce_add_sync(FULL, ties);
     near_t = __reduce_add_sync(FULL, near_t);
     par_ref = __reduce_add_sync(FULL, par_ref);
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         if (refined) atomicAdd(&p.cnt->refined, (unsigned long long)refined);
         if (ties) atomicAdd(&p.cnt->exact_ties, (unsigned long long)ties);
         if (near_t) atomicAdd(&p.cnt->near_tangent, (unsigned long long)near_t);
@@ -607,13 +695,18 @@ struct mpc_ctx {
     std::vector<int> scene_step_off;
     std::vector<double> origins;
     DevBuf ob_in, ob_f, ob_nv, step_obst_off, step_seg_begin, step_seg_end, scene_step_off_d, origins_d, sg_64, sg_f,
-        seg_scene, maxabs;
+        sg_box, seg_scene, maxabs;
+    int sg_stride = 32;
+    float maxabs_scene = 0.f;
     // queries
-    DevBuf q_d, cta_off_d, cand_d, mask_d, wl, cnt, flush;
+    DevBuf qpack_d, cand_d, res_d, wl, flush;
+    size_t qpack_cta_off = 0;
+    void *h_res = nullptr;
+    size_t h_res_cap = 0;
+    std::map<int, size_t> smem_attr;
     int wl_cap = 0;
     void *h_pin = nullptr;
     size_t h_pin_cap = 0;
-    Counters *h_cnt = nullptr;
     // prepared batch
     bool prepared = false;
     int B = 0, ctas = 0, mask_words = 0, gpc = 1, cap_o = 32, cap_s = 32, threads = 128;
@@ -682,8 +775,7 @@ extern "C" int mpc_create(int device, mpc_ctx **out) {
     if (ctx->prop.major < 9) return fail(ctx, MPC_E_CUDA, "device sm_%d%d lacks TMA bulk copies; built for sm_100a", ctx->prop.major, ctx->prop.minor);
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (auto &ev : ctx->ev) CU(cudaEventCreate(&ev));
-    CU(cudaMallocHost((void **)&ctx->h_cnt, sizeof(Counters)));
-    CU(ensure(ctx->cnt, sizeof(Counters)));
+    CU(ensure(ctx->res_d, sizeof(Counters) + 4096));
     CU(ensure(ctx->maxabs, sizeof(float)));
     CU(cudaMemsetAsync(ctx->maxabs.p, 0, sizeof(float), ctx->stream));
     ctx->wl_cap = 1 << 18;
@@ -700,12 +792,12 @@ extern "C" void mpc_destroy(mpc_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->lib_v, &ctx->lib_n, &ctx->lib_c, &ctx->lib_v64, &ctx->lib_nv, &ctx->slot_t, &ctx->sets,
                       &ctx->ob_in, &ctx->ob_f, &ctx->ob_nv, &ctx->step_obst_off, &ctx->step_seg_begin,
                       &ctx->step_seg_end, &ctx->scene_step_off_d, &ctx->origins_d, &ctx->sg_64, &ctx->sg_f,
-                      &ctx->seg_scene, &ctx->maxabs, &ctx->q_d, &ctx->cta_off_d, &ctx->cand_d, &ctx->mask_d, &ctx->wl,
-                      &ctx->cnt, &ctx->flush};
+                      &ctx->sg_box, &ctx->seg_scene, &ctx->maxabs, &ctx->qpack_d, &ctx->cand_d, &ctx->res_d, &ctx->wl,
+                      &ctx->flush};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
-    if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
+    if (ctx->h_res) cudaFreeHost(ctx->h_res);
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -843,6 +935,18 @@ extern "C" int mpc_upload_library(mpc_ctx *ctx, const double *verts, const int32
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+static inline unsigned morton16(unsigned x, unsigned y) {
+    auto spread = [](unsigned v) {
+        v &= 0xffff;
+        v = (v | (v << 8)) & 0x00ff00ff;
+        v = (v | (v << 4)) & 0x0f0f0f0f;
+        v = (v | (v << 2)) & 0x33333333;
+        v = (v | (v << 1)) & 0x55555555;
+        return v;
+    };
+    return spread(x) | (spread(y) << 1);
+}
+
 extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_off, const double *origins,
                               const int32_t *step_obst_off, const double *obst, const int32_t *obst_nv, int Vo,
                               const int32_t *step_seg_begin, const int32_t *step_seg_end, const double *segs, int nseg) {
@@ -859,8 +963,14 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     if (nobst > 0 && (!obst || !obst_nv)) return fail(ctx, MPC_E_ARG, "obstacle arrays missing");
     if (nobst > 0 && (Vo < 3 || Vo > MPC_MAX_OBST_VERTS)) return fail(ctx, MPC_E_LIMIT, "Vo=%d outside 3..%d", Vo, MPC_MAX_OBST_VERTS);
     if (nseg > 0 && !segs) return fail(ctx, MPC_E_ARG, "segment array missing");
+
+    // ---- boundary segments: every distinct [begin, end) range becomes a 32-aligned, spatially sorted (Morton order of
+    // the midpoints) block range on the device, so that k_check can skip whole blocks by their bounding box
     int max_o = 0, max_s = 0;
-    std::vector<int> seg_scene(std::max(nseg, 1), -1);
+    std::map<std::pair<int, int>, std::pair<int, int>> ranges;        // (begin, end) -> (device begin, scene)
+    std::vector<int> dev_begin(std::max(nsteps, 1), -1), dev_end(std::max(nsteps, 1), -1);
+    std::vector<double> dsegs;
+    std::vector<int> dscene;
     for (int s = 0; s < nscenes; s++)
         for (int k = scene_step_off[s]; k < scene_step_off[s + 1]; k++) {
             int no = step_obst_off[k + 1] - step_obst_off[k];
@@ -870,13 +980,37 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
             if (b < 0) continue;
             if (e < b || e > nseg) return fail(ctx, MPC_E_ARG, "segment range of step %d outside 0..%d", k, nseg);
             max_s = std::max(max_s, e - b);
-            // a range shared by all steps of a scene is marked once
-            if (e > b && seg_scene[b] == s && seg_scene[e - 1] == s) continue;
-            for (int g = b; g < e; g++) {
-                if (seg_scene[g] >= 0 && seg_scene[g] != s) return fail(ctx, MPC_E_ARG, "segment %d is shared by scenes %d and %d", g, seg_scene[g], s);
-                seg_scene[g] = s;
+            auto key = std::make_pair(b, e);
+            auto it = ranges.find(key);
+            if (it != ranges.end() && it->second.second != s) it = ranges.end();   // same range, other origin: copy
+            if (it == ranges.end()) {
+                const int n = e - b, start = (int)dscene.size();
+                std::vector<std::pair<unsigned, int>> order(n);
+                double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+                for (int g = b; g < e; g++) {
+                    double mx = 0.5 * (segs[4 * g] + segs[4 * g + 2]), my = 0.5 * (segs[4 * g + 1] + segs[4 * g + 3]);
+                    x0 = std::min(x0, mx); x1 = std::max(x1, mx); y0 = std::min(y0, my); y1 = std::max(y1, my);
+                }
+                const double sx = (x1 > x0) ? 65535.0 / (x1 - x0) : 0.0, sy = (y1 > y0) ? 65535.0 / (y1 - y0) : 0.0;
+                for (int g = b; g < e; g++) {
+                    double mx = 0.5 * (segs[4 * g] + segs[4 * g + 2]), my = 0.5 * (segs[4 * g + 1] + segs[4 * g + 3]);
+                    order[g - b] = {morton16((unsigned)((mx - x0) * sx), (unsigned)((my - y0) * sy)), g};
+                }
+                std::sort(order.begin(), order.end());
+                const int padded = (n + 31) / 32 * 32;
+                dsegs.resize((size_t)(start + padded) * 4, 0.0);
+                dscene.resize((size_t)(start + padded), -1);
+                for (int i = 0; i < n; i++) {
+                    const int g = order[i].second;
+                    for (int c = 0; c < 4; c++) dsegs[(size_t)(start + i) * 4 + c] = segs[4 * g + c];
+                    dscene[start + i] = s;
+                }
+                it = ranges.insert_or_assign(key, std::make_pair(start, s)).first;
             }
+            dev_begin[k] = it->second.first;
+            dev_end[k] = it->second.first + (e - b);
         }
+    const int nslots = (int)dscene.size();
     int vmax_used = 3;
     for (int o = 0; o < nobst; o++) {
         if (obst_nv[o] > Vo || obst_nv[o] < 0) return fail(ctx, MPC_E_ARG, "obst_nv[%d]=%d outside 0..%d", o, obst_nv[o], Vo);
@@ -884,7 +1018,7 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     }
     const int VB = vmax_used <= 4 ? 4 : 8;
     const int F = ob_fields(VB);
-    const int ob_stride = std::max(nobst, 1), sg_stride = std::max(nseg, 1);
+    const int ob_stride = std::max(nobst, 1), sg_stride = std::max(nslots, 32);
     CU(ensure(ctx->scene_step_off_d, (size_t)(nscenes + 1) * sizeof(int)));
     CU(ensure(ctx->origins_d, (size_t)nscenes * 2 * sizeof(double)));
     CU(ensure(ctx->step_obst_off, (size_t)(nsteps + 1) * sizeof(int)));
@@ -895,14 +1029,15 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     CU(ensure(ctx->ob_f, (size_t)ob_stride * F * sizeof(float4)));
     CU(ensure(ctx->sg_64, (size_t)sg_stride * 4 * sizeof(double)));
     CU(ensure(ctx->sg_f, (size_t)sg_stride * 2 * sizeof(float4)));
+    CU(ensure(ctx->sg_box, (size_t)(sg_stride / 32 + 1) * sizeof(float4)));
     CU(ensure(ctx->seg_scene, (size_t)sg_stride * sizeof(int)));
     cudaStream_t st = ctx->stream;
     CU(cudaMemcpyAsync(ctx->scene_step_off_d.p, scene_step_off, (size_t)(nscenes + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ctx->origins_d.p, origins, (size_t)nscenes * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ctx->step_obst_off.p, step_obst_off, (size_t)(nsteps + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
     if (nsteps) {
-        CU(cudaMemcpyAsync(ctx->step_seg_begin.p, step_seg_begin, (size_t)nsteps * sizeof(int), cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(ctx->step_seg_end.p, step_seg_end, (size_t)nsteps * sizeof(int), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->step_seg_begin.p, dev_begin.data(), (size_t)nsteps * sizeof(int), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->step_seg_end.p, dev_end.data(), (size_t)nsteps * sizeof(int), cudaMemcpyHostToDevice, st));
     }
     CU(cudaMemsetAsync(ctx->maxabs.p, 0, sizeof(float), st));
     if (nobst) {
@@ -922,15 +1057,18 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
                                                    (const int *)ctx->scene_step_off_d.p, nscenes, (const double *)ctx->origins_d.p, (float4 *)ctx->ob_f.p, ob_stride, (float *)ctx->maxabs.p);
         CU(cudaGetLastError());
     }
-    if (nseg) {
-        CU(cudaMemcpyAsync(ctx->sg_64.p, segs, (size_t)nseg * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(ctx->seg_scene.p, seg_scene.data(), (size_t)nseg * sizeof(int), cudaMemcpyHostToDevice, st));
-        k_stage_segs<<<(nseg + 127) / 128, 128, 0, st>>>(nseg, (const double *)ctx->sg_64.p, (const int *)ctx->seg_scene.p, (const double *)ctx->origins_d.p,
-                                                       (float4 *)ctx->sg_f.p, sg_stride, (float *)ctx->maxabs.p);
+    if (nslots) {
+        CU(cudaMemcpyAsync(ctx->sg_64.p, dsegs.data(), (size_t)nslots * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->seg_scene.p, dscene.data(), (size_t)nslots * sizeof(int), cudaMemcpyHostToDevice, st));
+        k_stage_segs<<<(nslots + 127) / 128, 128, 0, st>>>(nslots, (const double *)ctx->sg_64.p, (const int *)ctx->seg_scene.p, (const double *)ctx->origins_d.p,
+                                                         (float4 *)ctx->sg_f.p, sg_stride, (float4 *)ctx->sg_box.p, (float *)ctx->maxabs.p);
         CU(cudaGetLastError());
     }
-    CU(cudaStreamSynchronize(st));      // host buffers (incl. the local seg_scene) may be reused after return
-    ctx->nscenes = nscenes; ctx->nsteps = nsteps; ctx->nobst = nobst; ctx->nseg = nseg;
+    float m = 0.f;
+    CU(cudaMemcpyAsync(&m, ctx->maxabs.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));      // host buffers (incl. the local staging vectors) may be reused after return
+    ctx->maxabs_scene = m;
+    ctx->nscenes = nscenes; ctx->nsteps = nsteps; ctx->nobst = nobst; ctx->nseg = nslots; ctx->sg_stride = sg_stride;
     ctx->ob_vmax = VB; ctx->VB = VB; ctx->max_obst_step = max_o; ctx->max_seg_step = max_s;
     ctx->scene_step_off.assign(scene_step_off, scene_step_off + nscenes + 1);
     ctx->origins.assign(origins, origins + 2 * (size_t)nscenes);
@@ -940,6 +1078,9 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// result block on the device: [Counters (64 B)] [mask words]; one memset clears it, one copy brings it back
+static_assert(sizeof(Counters) == 64, "Counters is the 64-byte head of the result block");
+
 static KParams make_params(mpc_ctx *ctx) {
     KParams p;
     memset(&p, 0, sizeof p);
@@ -950,11 +1091,15 @@ static KParams make_params(mpc_ctx *ctx) {
     p.ob_stride = std::max(ctx->nobst, 1); p.ob_vmax = ctx->ob_vmax;
     p.step_obst_off = (const int *)ctx->step_obst_off.p; p.step_seg_begin = (const int *)ctx->step_seg_begin.p;
     p.step_seg_end = (const int *)ctx->step_seg_end.p;
-    p.sg_f = (const float4 *)ctx->sg_f.p; p.sg_64 = (const double *)ctx->sg_64.p; p.sg_stride = std::max(ctx->nseg, 1);
+    p.sg_f = (const float4 *)ctx->sg_f.p; p.sg_box = (const float4 *)ctx->sg_box.p; p.sg_64 = (const double *)ctx->sg_64.p;
+    p.sg_stride = ctx->sg_stride;
     p.maxabs_scene = (const float *)ctx->maxabs.p;
-    p.q = (const QDev *)ctx->q_d.p; p.cta_off = (const int *)ctx->cta_off_d.p; p.cand = (const int *)ctx->cand_d.p;
-    p.B = ctx->B; p.mask = (unsigned *)ctx->mask_d.p; p.wl = (int4 *)ctx->wl.p; p.wl_cap = ctx->wl_cap;
-    p.cnt = (Counters *)ctx->cnt.p; p.maxabs_query = ctx->maxabs_query; p.mode = ctx->mode;
+    char *qp = (char *)ctx->qpack_d.p;
+    p.q = (const QDev *)qp; p.cta_off = (const int *)(qp + ctx->qpack_cta_off); p.cand = (const int *)ctx->cand_d.p;
+    p.B = ctx->B;
+    p.cnt = (Counters *)ctx->res_d.p; p.mask = (unsigned *)((char *)ctx->res_d.p + sizeof(Counters));
+    p.wl = (int4 *)ctx->wl.p; p.wl_cap = ctx->wl_cap;
+    p.maxabs_query = ctx->maxabs_query; p.mode = ctx->mode;
     p.gpc = ctx->gpc; p.cap_o = ctx->cap_o; p.cap_s = ctx->cap_s;
     return p;
 }
@@ -962,8 +1107,12 @@ static KParams make_params(mpc_ctx *ctx) {
 template <int VA, int VB>
 static cudaError_t launch_check_vb(mpc_ctx *ctx, const KParams &p) {
     auto kern = (ctx->mode & MPC_MODE_COUNT_WORK) ? k_check<VA, VB, true> : k_check<VA, VB, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem);
-    if (e != cudaSuccess) return e;
+    const int key = VA * 1000 + VB * 10 + ((ctx->mode & MPC_MODE_COUNT_WORK) ? 1 : 0);
+    if (ctx->smem > 48 * 1024 && ctx->smem_attr[key] < ctx->smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem);
+        if (e != cudaSuccess) return e;
+        ctx->smem_attr[key] = ctx->smem;
+    }
     kern<<<ctx->ctas, ctx->threads, ctx->smem, ctx->stream>>>(p);
     return cudaGetLastError();
 }
@@ -983,8 +1132,7 @@ static int launch_all(mpc_ctx *ctx, cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t 
     KParams p = make_params(ctx);
     cudaStream_t st = ctx->stream;
     if (e0) CU(cudaEventRecord(e0, st));
-    CU(cudaMemsetAsync(ctx->cnt.p, 0, sizeof(Counters), st));
-    CU(cudaMemsetAsync(ctx->mask_d.p, 0, (size_t)std::max(ctx->mask_words, 1) * sizeof(unsigned), st));
+    CU(cudaMemsetAsync(ctx->res_d.p, 0, sizeof(Counters) + (size_t)ctx->mask_words * sizeof(unsigned), st));
     if (e1) CU(cudaEventRecord(e1, st));
     CU(launch_check(ctx, p));
     if (e2) CU(cudaEventRecord(e2, st));
@@ -1022,13 +1170,13 @@ extern "C" int mpc_prepare_query(mpc_ctx *ctx, int B, const mpc_query_desc *quer
     const int nwarps = ctx->threads / 32;
     int gpc = (int)((total_groups + (long long)sms * 6 - 1) / ((long long)sms * 6));
     gpc = std::max(1, std::min(gpc, GPC_MAX));
-    gpc = std::min(GPC_MAX, (gpc + nwarps - 1) / nwarps * nwarps);   // whole rounds of the CTA's warps
+    if (gpc > 1) gpc = std::min(GPC_MAX, (gpc + nwarps - 1) / nwarps * nwarps);   // whole rounds of the CTA's warps
     ctx->gpc = gpc;
     const int F = ob_fields(ctx->VB);
     ctx->cap_o = std::max(32, std::min((ctx->max_obst_step + 31) / 32 * 32, ctx->VB == 4 ? 320 : 160));
     ctx->cap_s = std::max(32, std::min((ctx->max_seg_step + 31) / 32 * 32, 512));
     ctx->smem = 16 + 3 * GPC_MAX * 4 + (size_t)ctx->cap_o * F * 16 + (size_t)ctx->cap_s * 32;
-    // pack: QDev[B], cta_off[B+1], explicit candidates
+    // pack: QDev[B], cta_off[B+1] (one copy), explicit candidates (second copy, only when present)
     size_t bytes_q = sizeof(QDev) * (size_t)std::max(B, 1), bytes_c = sizeof(int) * (size_t)(B + 1), bytes_i = sizeof(int) * (size_t)ncand;
     CU(ensure_pinned(ctx, bytes_q + bytes_c + bytes_i + 64));
     QDev *hq = (QDev *)ctx->h_pin;
@@ -1059,8 +1207,8 @@ extern "C" int mpc_prepare_query(mpc_ctx *ctx, int B, const mpc_query_desc *quer
     hcta[B] = (int)ctas;
     if (ctas > 0x7fffffffLL || words > 0x7fffffffLL) return fail(ctx, MPC_E_LIMIT, "batch too large");
     if (ncand) memcpy(hidx, cand_idx, bytes_i);
-    CU(ensure(ctx->q_d, bytes_q));
-    CU(ensure(ctx->cta_off_d, bytes_c));
+    CU(ensure(ctx->qpack_d, bytes_q + bytes_c));
+    ctx->qpack_cta_off = bytes_q;
     // candidate arena = staged sets followed by this call's explicit lists
     size_t arena = sizeof(int) * (size_t)std::max(ctx->set_total + ncand, 1);
     void *arena_before = ctx->cand_d.p;
@@ -1068,9 +1216,8 @@ extern "C" int mpc_prepare_query(mpc_ctx *ctx, int B, const mpc_query_desc *quer
     if ((ctx->cand_d.p != arena_before || !ctx->arena_valid) && ctx->set_total)
         CU(cudaMemcpyAsync(ctx->cand_d.p, ctx->sets.p, sizeof(int) * (size_t)ctx->set_total, cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->arena_valid = true;
-    CU(ensure(ctx->mask_d, sizeof(unsigned) * (size_t)std::max<long long>(words, 1)));
-    CU(cudaMemcpyAsync(ctx->q_d.p, hq, bytes_q, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->cta_off_d.p, hcta, bytes_c, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ensure(ctx->res_d, sizeof(Counters) + sizeof(unsigned) * (size_t)std::max<long long>(words, 1)));
+    CU(cudaMemcpyAsync(ctx->qpack_d.p, hq, bytes_q + bytes_c, cudaMemcpyHostToDevice, ctx->stream));
     if (ncand) CU(cudaMemcpyAsync((int *)ctx->cand_d.p + ctx->set_total, hidx, bytes_i, cudaMemcpyHostToDevice, ctx->stream));
     ctx->B = B; ctx->ctas = (int)ctas; ctx->mask_words = (int)words; ctx->mode = mode;
     ctx->maxabs_query = std::nextafter((float)maxq, INFINITY);
@@ -1080,7 +1227,7 @@ extern "C" int mpc_prepare_query(mpc_ctx *ctx, int B, const mpc_query_desc *quer
 
 static void fill_stats(mpc_ctx *ctx, mpc_stats *st, float ms, int kernels, int overflow) {
     if (!st) return;
-    const Counters &c = *ctx->h_cnt;
+    const Counters &c = *(const Counters *)ctx->h_res;
     st->pairs_nominal = (int64_t)c.pairs_nominal;
     st->refined_fp64 = (int64_t)c.refined;
     st->exact_ties = (int64_t)c.exact_ties;
@@ -1092,27 +1239,39 @@ static void fill_stats(mpc_ctx *ctx, mpc_stats *st, float ms, int kernels, int o
     st->ms_device = ms;
     st->ctas = ctx->ctas;
     st->kernels = kernels;
-    float m = 0.f;
-    cudaMemcpyAsync(&m, ctx->maxabs.p, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
-    cudaStreamSynchronize(ctx->stream);
-    st->tau = std::max(std::max(m, ctx->maxabs_query) / 131072.0f, 1e-7f);
+    st->tau = std::max(std::max(ctx->maxabs_scene, ctx->maxabs_query) / 131072.0f, 1e-7f);
 }
 
-// run the prepared batch once, growing the refinement list if it overflowed; leaves counters in h_cnt
-static int run_once(mpc_ctx *ctx, float *ms, int *kernels, int *overflow) {
+static cudaError_t ensure_result_host(mpc_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->h_res_cap) return cudaSuccess;
+    if (ctx->h_res) cudaFreeHost(ctx->h_res);
+    ctx->h_res = nullptr;
+    ctx->h_res_cap = 0;
+    size_t want = std::max<size_t>(bytes * 2, 4096);
+    cudaError_t e = cudaMallocHost(&ctx->h_res, want);
+    if (e == cudaSuccess) ctx->h_res_cap = want;
+    return e;
+}
+
+// run the prepared batch once and bring the result block (counters + mask) to pinned host memory with a single
+// synchronisation; grows the refinement list and re-runs if it overflowed
+static int run_once(mpc_ctx *ctx, float *ms, int *kernels, int *overflow, bool timed) {
     *overflow = 0;
     *kernels = 0;
+    const size_t bytes = sizeof(Counters) + (size_t)ctx->mask_words * sizeof(unsigned);
+    CU(ensure_result_host(ctx, bytes));
     for (int attempt = 0; attempt < 3; attempt++) {
-        int rc = launch_all(ctx, ctx->ev[0], nullptr, nullptr);
+        int rc = launch_all(ctx, timed ? ctx->ev[0] : nullptr, nullptr, nullptr);
         if (rc) return rc;
         *kernels += 2;
-        CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-        CU(cudaMemcpyAsync(ctx->h_cnt, ctx->cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+        if (timed) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+        CU(cudaMemcpyAsync(ctx->h_res, ctx->res_d.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
-        CU(cudaEventElapsedTime(ms, ctx->ev[0], ctx->ev[1]));
-        if (ctx->h_cnt->wl_count <= (unsigned)ctx->wl_cap) return MPC_OK;
+        if (timed) CU(cudaEventElapsedTime(ms, ctx->ev[0], ctx->ev[1]));
+        const Counters *c = (const Counters *)ctx->h_res;
+        if (c->wl_count <= (unsigned)ctx->wl_cap) return MPC_OK;
         *overflow = 1;
-        ctx->wl_cap = (int)std::min<unsigned long long>((unsigned long long)ctx->h_cnt->wl_count * 5 / 4 + 1024, 0x7fffffffULL / sizeof(int4));
+        ctx->wl_cap = (int)std::min<unsigned long long>((unsigned long long)c->wl_count * 5 / 4 + 1024, 0x7fffffffULL / sizeof(int4));
         CU(ensure(ctx->wl, sizeof(int4) * (size_t)ctx->wl_cap));
     }
     return fail(ctx, MPC_E_LIMIT, "refinement list still overflows at %d entries", ctx->wl_cap);
@@ -1126,12 +1285,9 @@ extern "C" int mpc_query(mpc_ctx *ctx, int B, const mpc_query_desc *queries, con
     if (mask_words > 0 && !out_mask) return fail(ctx, MPC_E_ARG, "out_mask missing");
     float ms = 0.f;
     int kernels = 0, overflow = 0;
-    rc = run_once(ctx, &ms, &kernels, &overflow);
+    rc = run_once(ctx, &ms, &kernels, &overflow, stats != nullptr);
     if (rc) return rc;
-    if (mask_words) {
-        CU(cudaMemcpyAsync(out_mask, ctx->mask_d.p, sizeof(unsigned) * (size_t)mask_words, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-    }
+    if (mask_words) memcpy(out_mask, (const char *)ctx->h_res + sizeof(Counters), sizeof(unsigned) * (size_t)mask_words);
     fill_stats(ctx, stats, ms, kernels, overflow);
     return MPC_OK;
 }
@@ -1142,7 +1298,7 @@ extern "C" int mpc_run_prepared(mpc_ctx *ctx, int iters, int flush_l2, float *ms
     CU(cudaSetDevice(ctx->device));
     float ms = 0.f;
     int kernels = 0, overflow = 0;
-    int rc = run_once(ctx, &ms, &kernels, &overflow);     // sizes the refinement list, warms nothing else up
+    int rc = run_once(ctx, &ms, &kernels, &overflow, true);     // sizes the refinement list
     if (rc) return rc;
     const size_t flush_bytes = 256u << 20;
     if (flush_l2) CU(ensure(ctx->flush, flush_bytes));
@@ -1163,7 +1319,8 @@ extern "C" int mpc_run_prepared(mpc_ctx *ctx, int iters, int flush_l2, float *ms
         ms = a;
         kernels += 2;
     }
-    CU(cudaMemcpyAsync(ctx->h_cnt, ctx->cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t bytes = sizeof(Counters) + (size_t)ctx->mask_words * sizeof(unsigned);
+    CU(cudaMemcpyAsync(ctx->h_res, ctx->res_d.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     fill_stats(ctx, stats, ms, kernels, overflow);
     return MPC_OK;
@@ -1174,7 +1331,7 @@ extern "C" int mpc_fetch_mask(mpc_ctx *ctx, uint32_t *out_mask, int mask_words) 
     if (!ctx->prepared) return fail(ctx, MPC_E_STATE, "no prepared batch");
     if (mask_words != ctx->mask_words) return fail(ctx, MPC_E_ARG, "mask_words=%d but the batch needs %d", mask_words, ctx->mask_words);
     if (mask_words) {
-        CU(cudaMemcpyAsync(out_mask, ctx->mask_d.p, sizeof(unsigned) * (size_t)mask_words, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(out_mask, (const char *)ctx->res_d.p + sizeof(Counters), sizeof(unsigned) * (size_t)mask_words, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }
     return MPC_OK;
