@@ -63,11 +63,12 @@ struct KParams {
     const int *lib_nv, *slot_t;
     int PJ, J, lib_vmax;
     // scenes
-    const float4 *ob_f;
+    const float4 *ob_f;          // [F-1][ob_stride] vertex and edge-line fields, slot layout (steps 32-aligned)
+    const float *ob_c;           // [3][ob_stride]   bounding circle x | y | r, slot layout
     const double *ob_v64;
     const int *ob_nv;
     int ob_stride, ob_vmax;
-    const int *step_obst_off, *step_seg_begin, *step_seg_end;
+    const int *step_obst_off, *step_obst_cnt, *step_seg_begin, *step_seg_end;
     const float4 *sg_f, *sg_box;
     const double *sg_64;
     int sg_stride;
@@ -80,7 +81,7 @@ struct KParams {
     int4 *wl;
     int wl_cap;
     Counters *cnt;
-    float maxabs_query;
+    float maxabs_query, lib_rmax;
     unsigned mode;
     int gpc, cap_o, cap_s;
 };
@@ -119,7 +120,25 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                  : "memory");
 }
 
-__host__ __device__ constexpr int ob_fields(int VB) { return VB / 2 + (VB * 3 + 3) / 4 + 1; }
+// packed float32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 -- two lanes of work per issued instruction)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+__host__ __device__ constexpr int ob_fields(int VB) { return VB / 2 + (VB * 3 + 3) / 4; }   // float4 fields (circle apart)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // staging kernels
@@ -137,21 +156,31 @@ __device__ __forceinline__ void atomic_max_pos_float(float *addr, float v) {
     atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
 }
 
+// one thread per obstacle *slot*: the obstacles of a step occupy a 32-aligned slot range [slot_off[k], slot_off[k+1]),
+// the tail is padding that can never be near anything.  Writes the float32 SoA records, the bounding circle arrays and
+// the CCW-normalised float64 copy (slot layout) for the tie-break pass.
 template <int VB>
-__global__ void k_stage_obst(int nobst, double *__restrict__ ob64, const int *__restrict__ ob_nv,
-                             const int *__restrict__ step_obst_off, int nsteps, const int *__restrict__ scene_step_off,
-                             int nscenes, const double *__restrict__ origins, float4 *__restrict__ ob_f, int stride,
-                             float *maxabs) {
-    int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= nobst) return;
+__global__ void k_stage_obst(int nslots, const double *__restrict__ src64, const int *__restrict__ src_nv,
+                             const int *__restrict__ src_off, const int *__restrict__ slot_off, int nsteps,
+                             const int *__restrict__ scene_step_off, int nscenes, const double *__restrict__ origins,
+                             float4 *__restrict__ ob_f, float *__restrict__ ob_c, double *__restrict__ ob64,
+                             int *__restrict__ ob_nv, int stride, float *maxabs) {
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= nslots) return;
     constexpr int F = ob_fields(VB);
-    int nv = ob_nv[o];
+    const int step = upper_bound_idx(slot_off, nsteps + 1, slot);
+    const int local = slot - slot_off[step];
+    const int cnt = src_off[step + 1] - src_off[step];
+    const int o = src_off[step] + local;
+    int nv = (local < cnt) ? src_nv[o] : 0;
     float out[F * 4];
-    double *v = ob64 + (size_t)o * VB * 2;
+    float ccx = FAR, ccy = FAR, ccr = 0.f;
+    double *v = ob64 + (size_t)slot * VB * 2;
     bool ok = nv >= 3 && nv <= VB;
     double x[VB], y[VB];
     if (ok) {
-        for (int k = 0; k < VB; k++) { x[k] = v[2 * (k < nv ? k : nv - 1)]; y[k] = v[2 * (k < nv ? k : nv - 1) + 1]; }
+        const double *sv = src64 + (size_t)o * VB * 2;
+        for (int k = 0; k < VB; k++) { x[k] = sv[2 * (k < nv ? k : nv - 1)]; y[k] = sv[2 * (k < nv ? k : nv - 1) + 1]; }
         double area = 0.0;
         for (int k = 0; k < nv; k++) {
             int k1 = (k + 1 == nv) ? 0 : k + 1;
@@ -167,13 +196,13 @@ __global__ void k_stage_obst(int nobst, double *__restrict__ ob64, const int *__
         }
     }
     if (!ok) {
-        // never near, never separating-axis-positive for anyone: a point far away
+        // never near, and "always separated" for whoever tests it anyway: a point far away
         for (int k = 0; k < VB; k++) { out[2 * k] = FAR; out[2 * k + 1] = FAR; }
         for (int k = 0; k < VB; k++) { out[VB * 2 + 3 * k] = 0.f; out[VB * 2 + 3 * k + 1] = 0.f; out[VB * 2 + 3 * k + 2] = -BIG; }
-        for (int k = VB * 5; k < F * 4 - 4; k++) out[k] = 0.f;
-        out[F * 4 - 4] = FAR; out[F * 4 - 3] = FAR; out[F * 4 - 2] = 0.f; out[F * 4 - 1] = 0.f;
+        for (int k = VB * 5; k < F * 4; k++) out[k] = 0.f;
+        for (int k = 0; k < VB * 2; k++) v[k] = 0.0;
+        nv = 0;
     } else {
-        int step = upper_bound_idx(step_obst_off, nsteps + 1, o);
         int sc = upper_bound_idx(scene_step_off, nscenes + 1, step);
         double ox = origins[2 * sc], oy = origins[2 * sc + 1];
         for (int k = 0; k < VB; k++) { v[2 * k] = x[k]; v[2 * k + 1] = y[k]; }
@@ -204,15 +233,18 @@ __global__ void k_stage_obst(int nobst, double *__restrict__ ob64, const int *__
             }
             out[VB * 2 + 3 * k] = nx; out[VB * 2 + 3 * k + 1] = ny; out[VB * 2 + 3 * k + 2] = c;
         }
-        for (int k = VB * 5; k < F * 4 - 4; k++) out[k] = 0.f;
-        out[F * 4 - 4] = (float)cx; out[F * 4 - 3] = (float)cy;
-        out[F * 4 - 2] = __double2float_ru(r * (1.0 + 1e-6) + m * 2.4e-7);
-        out[F * 4 - 1] = (float)nv;
+        for (int k = VB * 5; k < F * 4; k++) out[k] = 0.f;
+        ccx = (float)cx; ccy = (float)cy;
+        ccr = __double2float_ru(r * (1.0 + 1e-6) + m * 2.4e-7);
         atomic_max_pos_float(maxabs, __double2float_ru(m));
     }
+    ob_nv[slot] = nv;
 #pragma unroll
     for (int f = 0; f < F; f++)
-        ob_f[(size_t)f * stride + o] = make_float4(out[4 * f], out[4 * f + 1], out[4 * f + 2], out[4 * f + 3]);
+        ob_f[(size_t)f * stride + slot] = make_float4(out[4 * f], out[4 * f + 1], out[4 * f + 2], out[4 * f + 3]);
+    ob_c[slot] = ccx;
+    ob_c[(size_t)stride + slot] = ccy;
+    ob_c[(size_t)2 * stride + slot] = ccr;
 }
 
 __device__ __forceinline__ float warp_min(float v) {
@@ -312,7 +344,8 @@ __global__ void __launch_bounds__(128, 6) k_check(const KParams p) {
     unsigned *s_par = s_coll + GPC_MAX;
     unsigned *s_punc = s_par + GPC_MAX;
     float4 *s_ob = reinterpret_cast<float4 *>(smem_raw + 16 + 3 * GPC_MAX * 4);
-    float4 *s_sg = s_ob + F * p.cap_o;
+    float *s_c = reinterpret_cast<float *>(s_ob + F * p.cap_o);            // circle x | y | -(r + rmax)^2, cap_o each
+    float4 *s_sg = reinterpret_cast<float4 *>(s_c + 3 * p.cap_o);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
 
@@ -326,7 +359,8 @@ __global__ void __launch_bounds__(128, 6) k_check(const KParams p) {
     // reference guards: ind + time <= param['steps'] and ind + time < len(space)  (lowLevelPlannerManeuverAutomaton.py:120,122)
     if (t > Q->step_limit || t < 0 || t >= Q->nsteps) return;
     int step = Q->step0 + t;
-    const int o0 = p.step_obst_off[step], nobst = p.step_obst_off[step + 1] - o0;
+    // obstacles of the step: a 32-aligned slot range (padding slots are far away), `nobst` real ones
+    const int o0 = p.step_obst_off[step], nslot = p.step_obst_off[step + 1] - o0, nobst = p.step_obst_cnt[step];
     const int g0 = p.step_seg_begin[step];
     const bool has_region = g0 >= 0;
     const int nseg = has_region ? p.step_seg_end[step] - g0 : 0;
@@ -342,24 +376,37 @@ __global__ void __launch_bounds__(128, 6) k_check(const KParams p) {
     for (int i = tid; i < 3 * GPC_MAX; i += blockDim.x) s_coll[i] = 0;
     __syncthreads();
 
-    const int nph_o = (nobst + p.cap_o - 1) / p.cap_o, nph_s = (nseg + p.cap_s - 1) / p.cap_s;
+    const int nph_o = (nslot + p.cap_o - 1) / p.cap_o, nph_s = (nseg + p.cap_s - 1) / p.cap_s;
+    // cull radius shared by the whole CTA: largest library bounding radius + band (conservative for smaller polygons)
+    const float rcull = p.lib_rmax + 2.0f * tau;
     const int nphase = max(1, max(nph_o, nph_s));
     unsigned long long n_cull = 0, n_axis = 0;
 
     for (int ph = 0; ph < nphase; ph++) {
-        const int oc0 = ph * p.cap_o, ocn = max(0, min(nobst - oc0, p.cap_o));
+        const int oc0 = ph * p.cap_o, ocn = max(0, min(nslot - oc0, p.cap_o));       // multiple of 32
         const int sc0 = ph * p.cap_s, scn = max(0, min(nseg - sc0, p.cap_s));
         const bool loading = (ocn | scn) != 0;
         if (tid == 0 && loading) {
-            mbar_expect_tx(bar, (unsigned)(ocn * 16 * F + scn * 32));
-            if (ocn)
+            mbar_expect_tx(bar, (unsigned)(ocn * (16 * F + 12) + scn * 32));
+            if (ocn) {
                 for (int f = 0; f < F; f++)
                     tma_bulk_g2s(s_ob + f * p.cap_o, p.ob_f + (size_t)f * p.ob_stride + o0 + oc0, ocn * 16, bar);
+                for (int f = 0; f < 3; f++)
+                    tma_bulk_g2s(s_c + f * p.cap_o, p.ob_c + (size_t)f * p.ob_stride + o0 + oc0, ocn * 4, bar);
+            }
             if (scn)
                 for (int f = 0; f < 2; f++)
                     tma_bulk_g2s(s_sg + f * p.cap_s, p.sg_f + (size_t)f * p.sg_stride + g0 + sc0, scn * 16, bar);
         }
-        bool waited = false;
+        if (loading) {
+            mbar_wait(bar, ph & 1);
+            // third circle array: r  ->  -(r + rcull)^2, the constant term of the centre-line test
+            for (int i = tid; i < ocn; i += blockDim.x) {
+                float r = s_c[2 * p.cap_o + i] + rcull;
+                s_c[2 * p.cap_o + i] = -(r * r);
+            }
+            __syncthreads();
+        }
         for (int g = warp; g < ng; g += nwarps) {
             // ---- lane = one candidate primitive: load and transform its occupancy polygon -------------------------
             const int ci = (gbeg + g) * 32 + lane;
@@ -397,35 +444,33 @@ __global__ void __launch_bounds__(128, 6) k_check(const KParams p) {
                 unsigned w = __reduce_add_sync(FULL, active ? (unsigned)(nobst + nseg) : 0u);
                 if (lane == 0 && w) atomicAdd(&p.cnt->pairs_nominal, (unsigned long long)w);
             }
-            if (!waited && loading) { mbar_wait(bar, ph & 1); waited = true; }
 
             // ---- obstacles of this time step --------------------------------------------------------------------
-            const float4 *s_circ = s_ob + (F - 1) * p.cap_o;
+            const float4 *s_cx4 = reinterpret_cast<const float4 *>(s_c);
+            const float4 *s_cy4 = reinterpret_cast<const float4 *>(s_c + p.cap_o);
+            const float4 *s_cr4 = reinterpret_cast<const float4 *>(s_c + 2 * p.cap_o);
+            const f32x2 nax = pack2(-acx, -acx), nay = pack2(-acy, -acy);
             for (int ob = 0; ob < ocn; ob += 32) {
-                const int cnt = min(32, ocn - ob);
-                // axis 0: centre line with bounding radii.  One warp-broadcast LDS.128 per obstacle; the sign bit of
-                // e = |dc|^2 - (ra + rb + 2 tau)^2 is shifted into the hit word (bit 31-k <-> obstacle ob+k).
+                const int cnt = min(32, nobst - oc0 - ob);         // real obstacles in this block of 32 slots
+                // axis 0: centre line with bounding radii.  Three warp-broadcast LDS.128 bring four obstacles; packed
+                // FADD2/FFMA2 evaluate e = |dc|^2 - (rb + rcull)^2 for two of them per instruction and the sign bit
+                // of e is shifted into the hit word (bit 31-k <-> slot ob+k).
                 unsigned hits = 0;
                 if (!nocull) {
-                    if (cnt == 32) {
 #pragma unroll
-                        for (int k = 0; k < 32; k++) {
-                            float4 c = s_circ[ob + k];
-                            float dx = c.x - acx, dy = c.y - acy, rr = c.z + arr;
-                            float e = fmaf(dx, dx, fmaf(dy, dy, -(rr * rr)));
-                            hits = __funnelshift_l(__float_as_uint(e), hits, 1);
-                        }
-                    } else {
-                        for (int k = 0; k < cnt; k++) {
-                            float4 c = s_circ[ob + k];
-                            float dx = c.x - acx, dy = c.y - acy, rr = c.z + arr;
-                            float e = fmaf(dx, dx, fmaf(dy, dy, -(rr * rr)));
-                            hits = __funnelshift_l(__float_as_uint(e), hits, 1);
-                        }
-                        hits <<= 32 - cnt;
+                    for (int qd = 0; qd < 8; qd++) {
+                        const float4 X = s_cx4[(ob >> 2) + qd], Y = s_cy4[(ob >> 2) + qd], R = s_cr4[(ob >> 2) + qd];
+                        const f32x2 dx01 = add2(pack2(X.x, X.y), nax), dy01 = add2(pack2(Y.x, Y.y), nay);
+                        const f32x2 dx23 = add2(pack2(X.z, X.w), nax), dy23 = add2(pack2(Y.z, Y.w), nay);
+                        const f32x2 e01 = fma2(dx01, dx01, fma2(dy01, dy01, pack2(R.x, R.y)));
+                        const f32x2 e23 = fma2(dx23, dx23, fma2(dy23, dy23, pack2(R.z, R.w)));
+                        hits = __funnelshift_l((unsigned)e01, hits, 1);
+                        hits = __funnelshift_l((unsigned)(e01 >> 32), hits, 1);
+                        hits = __funnelshift_l((unsigned)e23, hits, 1);
+                        hits = __funnelshift_l((unsigned)(e23 >> 32), hits, 1);
                     }
                 } else {
-                    hits = ~((cnt == 32) ? 0u : (FULL >> cnt));
+                    hits = ~((cnt >= 32) ? 0u : (FULL >> cnt));
                 }
                 if (!active || (collide && !noexit)) hits = 0;
                 if (COUNT && active) n_cull += cnt;
@@ -554,10 +599,7 @@ __global__ void __launch_bounds__(128, 6) k_check(const KParams p) {
                 if (lane == 0 && word) atomicOr(p.mask + Q->mask_off + gbeg + g, word);
             }
         }
-        if (nphase > 1) {
-            if (!waited && loading) mbar_wait(bar, ph & 1);
-            __syncthreads();          // everyone is done with the tile before the next bulk copy overwrites it
-        }
+        if (nphase > 1) __syncthreads();      // everyone is done with the tile before the next bulk copy overwrites it
     }
     if (COUNT) {
         n_cull = __reduce_add_sync(FULL, (unsigned)n_cull) ;
@@ -685,6 +727,7 @@ struct mpc_ctx {
     bool have_lib = false;
     int P = 0, J = 0, lib_vmax = 0, VA = 4;
     double lib_radius = 0.0;
+    float lib_rmax = 0.f;
     DevBuf lib_v, lib_n, lib_c, lib_v64, lib_nv, slot_t, sets;
     std::vector<int> set_off;
     int nsets = 0, set_total = 0;
@@ -694,6 +737,8 @@ struct mpc_ctx {
     int nscenes = 0, nsteps = 0, nobst = 0, nseg = 0, ob_vmax = 4, VB = 4, max_obst_step = 0, max_seg_step = 0;
     std::vector<int> scene_step_off;
     std::vector<double> origins;
+    DevBuf ob_src, ob_src_nv, ob_src_off, ob_c, step_obst_cnt;
+    int ob_stride = 32;
     DevBuf ob_in, ob_f, ob_nv, step_obst_off, step_seg_begin, step_seg_end, scene_step_off_d, origins_d, sg_64, sg_f,
         sg_box, seg_scene, maxabs;
     int sg_stride = 32;
@@ -790,6 +835,7 @@ extern "C" void mpc_destroy(mpc_ctx *ctx) {
         cudaStreamSynchronize(ctx->stream);
     }
     DevBuf *bufs[] = {&ctx->lib_v, &ctx->lib_n, &ctx->lib_c, &ctx->lib_v64, &ctx->lib_nv, &ctx->slot_t, &ctx->sets,
+                      &ctx->ob_src, &ctx->ob_src_nv, &ctx->ob_src_off, &ctx->ob_c, &ctx->step_obst_cnt,
                       &ctx->ob_in, &ctx->ob_f, &ctx->ob_nv, &ctx->step_obst_off, &ctx->step_seg_begin,
                       &ctx->step_seg_end, &ctx->scene_step_off_d, &ctx->origins_d, &ctx->sg_64, &ctx->sg_f,
                       &ctx->sg_box, &ctx->seg_scene, &ctx->maxabs, &ctx->qpack_d, &ctx->cand_d, &ctx->res_d, &ctx->wl,
@@ -851,6 +897,7 @@ extern "C" int mpc_upload_library(mpc_ctx *ctx, const double *verts, const int32
     std::vector<double> h64(PJ * (size_t)VA * 2, 0.0);
     std::vector<int> hnv(PJ);
     double radius = 0.0;
+    float rmax = 0.f;
     for (size_t i = 0; i < PJ; i++) {
         int nv = nverts[i];
         double x[MPC_MAX_LIB_VERTS], y[MPC_MAX_LIB_VERTS];
@@ -895,6 +942,7 @@ extern "C" int mpc_upload_library(mpc_ctx *ctx, const double *verts, const int32
         }
         double rr = r * (1.0 + 1e-6) + std::hypot(cx, cy) * 2.4e-7 + 1e-7;
         hc[i] = make_float4((float)cx, (float)cy, std::nextafter((float)rr, INFINITY), (float)nv);
+        rmax = std::max(rmax, hc[i].z);
     }
     // note: a zero-length edge keeps normal (0,0); k_check turns its line into "never separating" only for e >= nv,
     // so give such edges the same treatment by dropping them here
@@ -927,7 +975,7 @@ extern "C" int mpc_upload_library(mpc_ctx *ctx, const double *verts, const int32
         if (total) CU(cudaMemcpyAsync(ctx->sets.p, set_idx, (size_t)total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->P = P; ctx->J = J; ctx->lib_vmax = VA; ctx->VA = VA; ctx->lib_radius = radius;
+    ctx->P = P; ctx->J = J; ctx->lib_vmax = VA; ctx->VA = VA; ctx->lib_radius = radius; ctx->lib_rmax = rmax;
     ctx->have_lib = true;
     ctx->prepared = false;
     ctx->arena_valid = false;
@@ -1018,15 +1066,27 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     }
     const int VB = vmax_used <= 4 ? 4 : 8;
     const int F = ob_fields(VB);
-    const int ob_stride = std::max(nobst, 1), sg_stride = std::max(nslots, 32);
+    // obstacle slots: the obstacles of step k live in the 32-aligned range [slot_off[k], slot_off[k+1])
+    std::vector<int> slot_off(nsteps + 1, 0), step_cnt(std::max(nsteps, 1), 0);
+    for (int k = 0; k < nsteps; k++) {
+        step_cnt[k] = step_obst_off[k + 1] - step_obst_off[k];
+        slot_off[k + 1] = slot_off[k] + (step_cnt[k] + 31) / 32 * 32;
+    }
+    const int noslots = slot_off[nsteps];
+    const int ob_stride = std::max(noslots, 32), sg_stride = std::max(nslots, 32);
     CU(ensure(ctx->scene_step_off_d, (size_t)(nscenes + 1) * sizeof(int)));
     CU(ensure(ctx->origins_d, (size_t)nscenes * 2 * sizeof(double)));
     CU(ensure(ctx->step_obst_off, (size_t)(nsteps + 1) * sizeof(int)));
     CU(ensure(ctx->step_seg_begin, (size_t)std::max(nsteps, 1) * sizeof(int)));
     CU(ensure(ctx->step_seg_end, (size_t)std::max(nsteps, 1) * sizeof(int)));
+    CU(ensure(ctx->ob_src, (size_t)std::max(nobst, 1) * VB * 2 * sizeof(double)));
+    CU(ensure(ctx->ob_src_nv, (size_t)std::max(nobst, 1) * sizeof(int)));
+    CU(ensure(ctx->ob_src_off, (size_t)(nsteps + 1) * sizeof(int)));
+    CU(ensure(ctx->step_obst_cnt, (size_t)std::max(nsteps, 1) * sizeof(int)));
     CU(ensure(ctx->ob_in, (size_t)ob_stride * VB * 2 * sizeof(double)));
     CU(ensure(ctx->ob_nv, (size_t)ob_stride * sizeof(int)));
     CU(ensure(ctx->ob_f, (size_t)ob_stride * F * sizeof(float4)));
+    CU(ensure(ctx->ob_c, (size_t)ob_stride * 3 * sizeof(float)));
     CU(ensure(ctx->sg_64, (size_t)sg_stride * 4 * sizeof(double)));
     CU(ensure(ctx->sg_f, (size_t)sg_stride * 2 * sizeof(float4)));
     CU(ensure(ctx->sg_box, (size_t)(sg_stride / 32 + 1) * sizeof(float4)));
@@ -1034,7 +1094,9 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     cudaStream_t st = ctx->stream;
     CU(cudaMemcpyAsync(ctx->scene_step_off_d.p, scene_step_off, (size_t)(nscenes + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ctx->origins_d.p, origins, (size_t)nscenes * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->step_obst_off.p, step_obst_off, (size_t)(nsteps + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->step_obst_off.p, slot_off.data(), (size_t)(nsteps + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->ob_src_off.p, step_obst_off, (size_t)(nsteps + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (nsteps) CU(cudaMemcpyAsync(ctx->step_obst_cnt.p, step_cnt.data(), (size_t)nsteps * sizeof(int), cudaMemcpyHostToDevice, st));
     if (nsteps) {
         CU(cudaMemcpyAsync(ctx->step_seg_begin.p, dev_begin.data(), (size_t)nsteps * sizeof(int), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(ctx->step_seg_end.p, dev_end.data(), (size_t)nsteps * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -1042,19 +1104,23 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     CU(cudaMemsetAsync(ctx->maxabs.p, 0, sizeof(float), st));
     if (nobst) {
         if (Vo == VB) {
-            CU(cudaMemcpyAsync(ctx->ob_in.p, obst, (size_t)nobst * VB * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(ctx->ob_src.p, obst, (size_t)nobst * VB * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
         } else {   // caller's vertex stride differs from the kernel's: repack rows
-            CU(cudaMemcpy2DAsync(ctx->ob_in.p, (size_t)VB * 2 * sizeof(double), obst, (size_t)Vo * 2 * sizeof(double),
+            CU(cudaMemcpy2DAsync(ctx->ob_src.p, (size_t)VB * 2 * sizeof(double), obst, (size_t)Vo * 2 * sizeof(double),
                                  (size_t)std::min(Vo, VB) * 2 * sizeof(double), nobst, cudaMemcpyHostToDevice, st));
         }
-        CU(cudaMemcpyAsync(ctx->ob_nv.p, obst_nv, (size_t)nobst * sizeof(int), cudaMemcpyHostToDevice, st));
-        int blocks = (nobst + 127) / 128;
+        CU(cudaMemcpyAsync(ctx->ob_src_nv.p, obst_nv, (size_t)nobst * sizeof(int), cudaMemcpyHostToDevice, st));
+        int blocks = (noslots + 127) / 128;
         if (VB == 4)
-            k_stage_obst<4><<<blocks, 128, 0, st>>>(nobst, (double *)ctx->ob_in.p, (const int *)ctx->ob_nv.p, (const int *)ctx->step_obst_off.p, nsteps,
-                                                   (const int *)ctx->scene_step_off_d.p, nscenes, (const double *)ctx->origins_d.p, (float4 *)ctx->ob_f.p, ob_stride, (float *)ctx->maxabs.p);
+            k_stage_obst<4><<<blocks, 128, 0, st>>>(noslots, (const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_src_off.p,
+                                                   (const int *)ctx->step_obst_off.p, nsteps, (const int *)ctx->scene_step_off_d.p, nscenes,
+                                                   (const double *)ctx->origins_d.p, (float4 *)ctx->ob_f.p, (float *)ctx->ob_c.p, (double *)ctx->ob_in.p,
+                                                   (int *)ctx->ob_nv.p, ob_stride, (float *)ctx->maxabs.p);
         else
-            k_stage_obst<8><<<blocks, 128, 0, st>>>(nobst, (double *)ctx->ob_in.p, (const int *)ctx->ob_nv.p, (const int *)ctx->step_obst_off.p, nsteps,
-                                                   (const int *)ctx->scene_step_off_d.p, nscenes, (const double *)ctx->origins_d.p, (float4 *)ctx->ob_f.p, ob_stride, (float *)ctx->maxabs.p);
+            k_stage_obst<8><<<blocks, 128, 0, st>>>(noslots, (const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_src_off.p,
+                                                   (const int *)ctx->step_obst_off.p, nsteps, (const int *)ctx->scene_step_off_d.p, nscenes,
+                                                   (const double *)ctx->origins_d.p, (float4 *)ctx->ob_f.p, (float *)ctx->ob_c.p, (double *)ctx->ob_in.p,
+                                                   (int *)ctx->ob_nv.p, ob_stride, (float *)ctx->maxabs.p);
         CU(cudaGetLastError());
     }
     if (nslots) {
@@ -1069,6 +1135,7 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     CU(cudaStreamSynchronize(st));      // host buffers (incl. the local staging vectors) may be reused after return
     ctx->maxabs_scene = m;
     ctx->nscenes = nscenes; ctx->nsteps = nsteps; ctx->nobst = nobst; ctx->nseg = nslots; ctx->sg_stride = sg_stride;
+    ctx->ob_stride = ob_stride;
     ctx->ob_vmax = VB; ctx->VB = VB; ctx->max_obst_step = max_o; ctx->max_seg_step = max_s;
     ctx->scene_step_off.assign(scene_step_off, scene_step_off + nscenes + 1);
     ctx->origins.assign(origins, origins + 2 * (size_t)nscenes);
@@ -1087,9 +1154,11 @@ static KParams make_params(mpc_ctx *ctx) {
     p.lib_v = (const float4 *)ctx->lib_v.p; p.lib_n = (const float4 *)ctx->lib_n.p; p.lib_c = (const float4 *)ctx->lib_c.p;
     p.lib_v64 = (const double *)ctx->lib_v64.p; p.lib_nv = (const int *)ctx->lib_nv.p; p.slot_t = (const int *)ctx->slot_t.p;
     p.PJ = ctx->P * ctx->J; p.J = ctx->J; p.lib_vmax = ctx->lib_vmax;
-    p.ob_f = (const float4 *)ctx->ob_f.p; p.ob_v64 = (const double *)ctx->ob_in.p; p.ob_nv = (const int *)ctx->ob_nv.p;
-    p.ob_stride = std::max(ctx->nobst, 1); p.ob_vmax = ctx->ob_vmax;
-    p.step_obst_off = (const int *)ctx->step_obst_off.p; p.step_seg_begin = (const int *)ctx->step_seg_begin.p;
+    p.ob_f = (const float4 *)ctx->ob_f.p; p.ob_c = (const float *)ctx->ob_c.p;
+    p.ob_v64 = (const double *)ctx->ob_in.p; p.ob_nv = (const int *)ctx->ob_nv.p;
+    p.ob_stride = ctx->ob_stride; p.ob_vmax = ctx->ob_vmax;
+    p.step_obst_off = (const int *)ctx->step_obst_off.p; p.step_obst_cnt = (const int *)ctx->step_obst_cnt.p;
+    p.step_seg_begin = (const int *)ctx->step_seg_begin.p;
     p.step_seg_end = (const int *)ctx->step_seg_end.p;
     p.sg_f = (const float4 *)ctx->sg_f.p; p.sg_box = (const float4 *)ctx->sg_box.p; p.sg_64 = (const double *)ctx->sg_64.p;
     p.sg_stride = ctx->sg_stride;
@@ -1099,7 +1168,7 @@ static KParams make_params(mpc_ctx *ctx) {
     p.B = ctx->B;
     p.cnt = (Counters *)ctx->res_d.p; p.mask = (unsigned *)((char *)ctx->res_d.p + sizeof(Counters));
     p.wl = (int4 *)ctx->wl.p; p.wl_cap = ctx->wl_cap;
-    p.maxabs_query = ctx->maxabs_query; p.mode = ctx->mode;
+    p.maxabs_query = ctx->maxabs_query; p.lib_rmax = ctx->lib_rmax; p.mode = ctx->mode;
     p.gpc = ctx->gpc; p.cap_o = ctx->cap_o; p.cap_s = ctx->cap_s;
     return p;
 }
@@ -1175,7 +1244,7 @@ extern "C" int mpc_prepare_query(mpc_ctx *ctx, int B, const mpc_query_desc *quer
     const int F = ob_fields(ctx->VB);
     ctx->cap_o = std::max(32, std::min((ctx->max_obst_step + 31) / 32 * 32, ctx->VB == 4 ? 320 : 160));
     ctx->cap_s = std::max(32, std::min((ctx->max_seg_step + 31) / 32 * 32, 512));
-    ctx->smem = 16 + 3 * GPC_MAX * 4 + (size_t)ctx->cap_o * F * 16 + (size_t)ctx->cap_s * 32;
+    ctx->smem = 16 + 3 * GPC_MAX * 4 + (size_t)ctx->cap_o * (F * 16 + 12) + (size_t)ctx->cap_s * 32;
     // pack: QDev[B], cta_off[B+1] (one copy), explicit candidates (second copy, only when present)
     size_t bytes_q = sizeof(QDev) * (size_t)std::max(B, 1), bytes_c = sizeof(int) * (size_t)(B + 1), bytes_i = sizeof(int) * (size_t)ncand;
     CU(ensure_pinned(ctx, bytes_q + bytes_c + bytes_i + 64));
