@@ -38,7 +38,7 @@ O = O_LANES * SLOTS
 CHECKS_PER_QUERY = P * O * T
 FLOP_PER_CHECK = 304            # rectangle x rectangle SAT, a = 8 axes, a*(4a+6)
 SAT_FLOP_EXECUTED = 160         # this kernel's full 4x4 test: 64 FMA (2 flop) + 24 min + 8 max
-CULL_FLOP_EXECUTED = 8          # centre-line axis: 2 sub, 1 add, 1 mul, 1 fma (2), 1 mul, 1 compare
+CULL_FLOP_EXECUTED = 6          # centre-line axis per pair: 2 add + 2 fma (packed FADD2/FFMA2: two pairs per instruction)
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # no FP32 entry in MEASURED_PEAKS.json: derived from its sm_max_mhz
 METRIC = "primitive x obstacle x timestep collision checks/sec"
 
@@ -308,7 +308,7 @@ def main():
             "gpu_launches": int(args.steps * 3),
             "gpu_launches_what": "per timed step: k_fill_u32 (L2 flush, outside the event bracket), k_check, k_refine",
             "clocks": clocks,
-            "roofline": {"bound": "fp32", "kernel": "k_check<4,4>", "achieved": algo_tflops, "peak": FP32_PEAK_TFLOPS,
+            "roofline": {"bound": "fp32", "kernel": "k_check<4,4,0,0>", "achieved": algo_tflops, "peak": FP32_PEAK_TFLOPS,
                          "unit": "TFLOP/s", "frac": algo_tflops / FP32_PEAK_TFLOPS, "traffic": None,
                          "peak_source": "derived 148 SM x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json has no FP32 "
                                         "figure); algorithmic = 304 flop/check (SURVEY 8d) x checks per launch",

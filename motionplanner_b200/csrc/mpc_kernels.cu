@@ -298,56 +298,85 @@ __device__ __forceinline__ void push_work(const KParams &p, int q, int ci, int j
     if (idx < (unsigned)p.wl_cap) p.wl[idx] = make_int4(q, ci, j | (kind << 16), obj);
 }
 
-// full separating-axis test of the lane's polygon against obstacle record `o` of the shared-memory tile.
-// returns the signed separation (max over all edge axes of the minimum vertex distance); > 0 apart.
-template <int VA, int VB>
-__device__ __forceinline__ float sat_obstacle(const float (&ax)[VA], const float (&ay)[VA], const float (&anx)[VA],
-                                              const float (&any_)[VA], const float (&ac)[VA], const float4 *s_ob,
-                                              int cap_o, int o) {
-    float bx[VB], by[VB];
+// A polygon record in shared memory is SoA by float4 field: V/2 fields of vertex pairs (x0,y0,x1,y1), then
+// ceil(3V/4) fields holding the packed edge lines (nx, ny, c) -- the same layout for obstacle records (staged by
+// k_stage_obst) and for the transformed occupancy polygons the warps write themselves.
+template <int V>
+struct PolyRegs {
+    float x[V], y[V], ln[((V * 3 + 3) / 4) * 4];
+    __device__ __forceinline__ void load(const float4 *rec, int stride, int i) {
 #pragma unroll
-    for (int h = 0; h < VB / 2; h++) {
-        float4 v = s_ob[h * cap_o + o];
-        bx[2 * h] = v.x; by[2 * h] = v.y; bx[2 * h + 1] = v.z; by[2 * h + 1] = v.w;
+        for (int h = 0; h < V / 2; h++) {
+            float4 v = rec[h * stride + i];
+            x[2 * h] = v.x; y[2 * h] = v.y; x[2 * h + 1] = v.z; y[2 * h + 1] = v.w;
+        }
+#pragma unroll
+        for (int h = 0; h < (V * 3 + 3) / 4; h++) {
+            float4 v = rec[(V / 2 + h) * stride + i];
+            ln[4 * h] = v.x; ln[4 * h + 1] = v.y; ln[4 * h + 2] = v.z; ln[4 * h + 3] = v.w;
+        }
     }
+};
+
+// signed separation of two convex polygons: max over all edge axes of the minimum vertex distance (> 0 apart)
+template <int VA, int VB>
+__device__ __forceinline__ float sat_polys(const PolyRegs<VA> &A, const PolyRegs<VB> &B) {
     float sep = -BIG;
 #pragma unroll
     for (int e = 0; e < VA; e++) {
+        const float nx = A.ln[3 * e], ny = A.ln[3 * e + 1], c = A.ln[3 * e + 2];
         float mn = BIG;
 #pragma unroll
-        for (int k = 0; k < VB; k++) mn = fminf(mn, fmaf(anx[e], bx[k], fmaf(any_[e], by[k], -ac[e])));
+        for (int k = 0; k < VB; k++) mn = fminf(mn, fmaf(nx, B.x[k], fmaf(ny, B.y[k], -c)));
         sep = fmaxf(sep, mn);
-    }
-    float ln[((VB * 3 + 3) / 4) * 4];
-#pragma unroll
-    for (int h = 0; h < (VB * 3 + 3) / 4; h++) {
-        float4 v = s_ob[(VB / 2 + h) * cap_o + o];
-        ln[4 * h] = v.x; ln[4 * h + 1] = v.y; ln[4 * h + 2] = v.z; ln[4 * h + 3] = v.w;
     }
 #pragma unroll
     for (int e = 0; e < VB; e++) {
-        float nx = ln[3 * e], ny = ln[3 * e + 1], c = ln[3 * e + 2];
+        const float nx = B.ln[3 * e], ny = B.ln[3 * e + 1], c = B.ln[3 * e + 2];
         float mn = BIG;
 #pragma unroll
-        for (int k = 0; k < VA; k++) mn = fminf(mn, fmaf(nx, ax[k], fmaf(ny, ay[k], -c)));
+        for (int k = 0; k < VA; k++) mn = fminf(mn, fmaf(nx, A.x[k], fmaf(ny, A.y[k], -c)));
         sep = fmaxf(sep, mn);
     }
     return sep;
 }
 
-template <int VA, int VB, bool COUNT>
-__global__ void __launch_bounds__(128, 6) k_check(const KParams p) {
-    constexpr int F = ob_fields(VB);
+// signed separation of a convex polygon and a segment (a 2-gon): edges of A against the two end points, the
+// segment's line against the vertices of A on either side
+template <int VA>
+__device__ __forceinline__ float sat_segment(const PolyRegs<VA> &A, const float4 sa, const float4 sl) {
+    float sep = -BIG, mn = BIG, mx = -BIG;
+#pragma unroll
+    for (int e = 0; e < VA; e++) {
+        const float nx = A.ln[3 * e], ny = A.ln[3 * e + 1], c = A.ln[3 * e + 2];
+        const float d0 = fmaf(nx, sa.x, fmaf(ny, sa.y, -c)), d1 = fmaf(nx, sa.z, fmaf(ny, sa.w, -c));
+        sep = fmaxf(sep, fminf(d0, d1));
+        const float d = fmaf(sl.x, A.x[e], fmaf(sl.y, A.y[e], -sl.z));
+        mn = fminf(mn, d);
+        mx = fmaxf(mx, d);
+    }
+    return fmaxf(sep, fmaxf(mn, -mx));
+}
+
+constexpr int K_THREADS = 256;      // 8 warps share one staged tile
+constexpr int QCAP = 64;            // per-warp queue of (lane, record) pairs that passed axis 0
+
+template <int VA, int VB, bool COUNT, bool NOCULL>
+__global__ void __launch_bounds__(K_THREADS, NOCULL ? 2 : 4) k_check(const KParams p) {
+    constexpr int F = ob_fields(VB), FA = ob_fields(VA), NW = K_THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_raw);
     unsigned *s_coll = reinterpret_cast<unsigned *>(smem_raw + 16);
     unsigned *s_par = s_coll + GPC_MAX;
     unsigned *s_punc = s_par + GPC_MAX;
-    float4 *s_ob = reinterpret_cast<float4 *>(smem_raw + 16 + 3 * GPC_MAX * 4);
-    float *s_c = reinterpret_cast<float *>(s_ob + F * p.cap_o);            // circle x | y | -(r + rmax)^2, cap_o each
-    float4 *s_sg = reinterpret_cast<float4 *>(s_c + 3 * p.cap_o);
+    unsigned *s_q = s_punc + GPC_MAX;                                          // [NW][QCAP]
+    float4 *s_A = reinterpret_cast<float4 *>(s_q + NW * QCAP);                 // [NW][FA][32] occupancy polygons
+    float4 *s_ob = s_A + NW * FA * 32;                                         // [F][cap_o] obstacle records
+    float *s_c = reinterpret_cast<float *>(s_ob + F * p.cap_o);                // circle x | y | -(r + rcull)^2
+    float4 *s_sg = reinterpret_cast<float4 *>(s_c + 3 * p.cap_o);              // [2][cap_s] segments
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     // which (query, slot, chunk) is this CTA
     int q = upper_bound_idx(p.cta_off, p.B + 1, (int)blockIdx.x);
@@ -370,17 +399,19 @@ __global__ void __launch_bounds__(128, 6) k_check(const KParams p) {
     const float lx = Q->lx, ly = Q->ly, lc = Q->lc, ls = Q->ls;
     // float32 error band: every float32 signed distance below is within tau of its float64 value
     const float tau = fmaxf(fmaxf(*p.maxabs_scene, p.maxabs_query) * (1.0f / 131072.0f), 1e-7f);
-    const bool noexit = p.mode & MPC_MODE_NO_EARLY_EXIT, nocull = p.mode & MPC_MODE_NO_CULL;
+    const bool noexit = p.mode & MPC_MODE_NO_EARLY_EXIT;
 
     if (tid == 0) mbar_init(bar, 1);
-    for (int i = tid; i < 3 * GPC_MAX; i += blockDim.x) s_coll[i] = 0;
+    for (int i = tid; i < 3 * GPC_MAX; i += K_THREADS) s_coll[i] = 0;
     __syncthreads();
 
     const int nph_o = (nslot + p.cap_o - 1) / p.cap_o, nph_s = (nseg + p.cap_s - 1) / p.cap_s;
+    const int nphase = max(1, max(nph_o, nph_s));
     // cull radius shared by the whole CTA: largest library bounding radius + band (conservative for smaller polygons)
     const float rcull = p.lib_rmax + 2.0f * tau;
-    const int nphase = max(1, max(nph_o, nph_s));
-    unsigned long long n_cull = 0, n_axis = 0;
+    unsigned n_cull = 0, n_axis = 0;
+    float4 *sA = s_A + warp * FA * 32;
+    unsigned *sq = s_q + warp * QCAP;
 
     for (int ph = 0; ph < nphase; ph++) {
         const int oc0 = ph * p.cap_o, ocn = max(0, min(nslot - oc0, p.cap_o));       // multiple of 32
@@ -401,14 +432,14 @@ __global__ void __launch_bounds__(128, 6) k_check(const KParams p) {
         if (loading) {
             mbar_wait(bar, ph & 1);
             // third circle array: r  ->  -(r + rcull)^2, the constant term of the centre-line test
-            for (int i = tid; i < ocn; i += blockDim.x) {
+            for (int i = tid; i < ocn; i += K_THREADS) {
                 float r = s_c[2 * p.cap_o + i] + rcull;
                 s_c[2 * p.cap_o + i] = -(r * r);
             }
             __syncthreads();
         }
-        for (int g = warp; g < ng; g += nwarps) {
-            // ---- lane = one candidate primitive: load and transform its occupancy polygon -------------------------
+        for (int g = warp; g < ng; g += NW) {
+            // ---- lane = one candidate primitive: transform its occupancy polygon, park it in shared memory ----------
             const int ci = (gbeg + g) * 32 + lane;
             bool active = ci < cand_cnt;
             int pj = 0;
@@ -417,46 +448,137 @@ __global__ void __launch_bounds__(128, 6) k_check(const KParams p) {
             if (active) cc = __ldg(p.lib_c + pj);
             const int nv = (int)cc.w;
             active = active && nv > 0;
-            float ax[VA], ay[VA], anx[VA], any_[VA], ac[VA];
+            {
+                float ax[VA], ay[VA], ln[((VA * 3 + 3) / 4) * 4];
 #pragma unroll
-            for (int h = 0; h < VA / 2; h++) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f), n = v;
-                if (active) { v = __ldg(p.lib_v + (size_t)h * p.PJ + pj); n = __ldg(p.lib_n + (size_t)h * p.PJ + pj); }
-                ax[2 * h] = fmaf(lc, v.x, fmaf(-ls, v.y, lx));
-                ay[2 * h] = fmaf(ls, v.x, fmaf(lc, v.y, ly));
-                ax[2 * h + 1] = fmaf(lc, v.z, fmaf(-ls, v.w, lx));
-                ay[2 * h + 1] = fmaf(ls, v.z, fmaf(lc, v.w, ly));
-                anx[2 * h] = fmaf(lc, n.x, -ls * n.y);
-                any_[2 * h] = fmaf(ls, n.x, lc * n.y);
-                anx[2 * h + 1] = fmaf(lc, n.z, -ls * n.w);
-                any_[2 * h + 1] = fmaf(ls, n.z, lc * n.w);
+                for (int i = 0; i < ((VA * 3 + 3) / 4) * 4; i++) ln[i] = 0.f;
+#pragma unroll
+                for (int h = 0; h < VA / 2; h++) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), n = v;
+                    if (active) { v = __ldg(p.lib_v + (size_t)h * p.PJ + pj); n = __ldg(p.lib_n + (size_t)h * p.PJ + pj); }
+                    ax[2 * h] = fmaf(lc, v.x, fmaf(-ls, v.y, lx));
+                    ay[2 * h] = fmaf(ls, v.x, fmaf(lc, v.y, ly));
+                    ax[2 * h + 1] = fmaf(lc, v.z, fmaf(-ls, v.w, lx));
+                    ay[2 * h + 1] = fmaf(ls, v.z, fmaf(lc, v.w, ly));
+                    ln[6 * h] = fmaf(lc, n.x, -ls * n.y);
+                    ln[6 * h + 1] = fmaf(ls, n.x, lc * n.y);
+                    ln[6 * h + 3] = fmaf(lc, n.z, -ls * n.w);
+                    ln[6 * h + 4] = fmaf(ls, n.z, lc * n.w);
+                }
+#pragma unroll
+                for (int e = 0; e < VA; e++)       // line offset; an edge beyond nv never separates
+                    ln[3 * e + 2] = (e < nv) ? fmaf(ln[3 * e], ax[e], ln[3 * e + 1] * ay[e]) : BIG;
+                __syncwarp();                       // previous group's readers are done with sA
+#pragma unroll
+                for (int h = 0; h < VA / 2; h++) sA[h * 32 + lane] = make_float4(ax[2 * h], ay[2 * h], ax[2 * h + 1], ay[2 * h + 1]);
+#pragma unroll
+                for (int h = 0; h < (VA * 3 + 3) / 4; h++)
+                    sA[(VA / 2 + h) * 32 + lane] = make_float4(ln[4 * h], ln[4 * h + 1], ln[4 * h + 2], ln[4 * h + 3]);
+                __syncwarp();
             }
-#pragma unroll
-            for (int e = 0; e < VA; e++) ac[e] = (e < nv) ? fmaf(anx[e], ax[e], any_[e] * ay[e]) : BIG;
             const float acx = active ? fmaf(lc, cc.x, fmaf(-ls, cc.y, lx)) : -FAR;
             const float acy = active ? fmaf(ls, cc.x, fmaf(lc, cc.y, ly)) : -FAR;
             const float arr = cc.z + 2.0f * tau;
 
             bool collide = (s_coll[g] >> lane) & 1u;
             bool par = false, punc = false;
+            unsigned qn = 0;                        // entries in this warp's queue (warp-uniform)
 
             if (ph == 0) {   // statistic: nominal pair count of this tile
                 unsigned w = __reduce_add_sync(FULL, active ? (unsigned)(nobst + nseg) : 0u);
                 if (lane == 0 && w) atomicAdd(&p.cnt->pairs_nominal, (unsigned long long)w);
             }
 
+            // queue entry = (owner lane << 16) | record index in the tile.  Draining evaluates up to 32 queued pairs at
+            // once, one per lane, whichever lane they belong to: the full separating-axis test runs with all lanes busy
+            // although only ~1 % of the pairs reach it.
+            auto push_hits = [&](unsigned &hits, int base, auto &&drain) {
+                while (__any_sync(FULL, hits != 0)) {
+                    if (qn >= 32) drain();
+                    const bool has = hits != 0;
+                    const unsigned bal = __ballot_sync(FULL, has);
+                    if (has) {
+                        const int k = __clz(hits);
+                        hits &= ~(0x80000000u >> k);
+                        sq[qn + __popc(bal & lt_mask)] = ((unsigned)lane << 16) | (unsigned)(base + k);
+                    }
+                    qn += __popc(bal);
+                    __syncwarp();
+                    if (collide && !noexit) hits = 0;
+                }
+            };
+            auto pop_batch = [&](unsigned &ent) -> bool {       // take min(32, qn) entries, compact the rest
+                const int n = min(32u, qn);
+                const bool have = lane < n;
+                ent = have ? sq[lane] : 0u;
+                unsigned rest = (lane + 32 < (int)qn) ? sq[lane + 32] : 0u;
+                __syncwarp();
+                if (lane + 32 < (int)qn) sq[lane] = rest;
+                __syncwarp();
+                qn -= n;
+                return have;
+            };
+            auto drain_obst = [&]() {
+                unsigned ent;
+                const bool have = pop_batch(ent);
+                const int src = ent >> 16, slot = ent & 0xffff;
+                float sep = BIG;
+                if (have) {
+                    PolyRegs<VA> A;
+                    PolyRegs<VB> B;
+                    A.load(sA, 32, src);
+                    B.load(s_ob, p.cap_o, slot);
+                    sep = sat_polys<VA, VB>(A, B);
+                    if (COUNT) n_axis++;
+                }
+                const bool hit = have && sep < -tau;
+                if (have && !hit && !(sep > tau)) push_work(p, q, (gbeg + g) * 32 + src, j, KIND_OBST, o0 + oc0 + slot);
+                const unsigned m = __reduce_or_sync(FULL, hit ? (1u << src) : 0u);
+                collide |= (m >> lane) & 1u;
+            };
+            auto drain_seg = [&]() {
+                unsigned ent;
+                const bool have = pop_batch(ent);
+                const int src = ent >> 16, k = ent & 0xffff;
+                float sep = BIG;
+                if (have) {
+                    PolyRegs<VA> A;
+                    A.load(sA, 32, src);
+                    sep = sat_segment<VA>(A, s_sg[k], s_sg[p.cap_s + k]);
+                    if (COUNT) n_axis++;
+                }
+                const bool hit = have && sep < -tau;
+                if (have && !hit && !(sep > tau)) push_work(p, q, (gbeg + g) * 32 + src, j, KIND_SEG, g0 + sc0 + k);
+                const unsigned m = __reduce_or_sync(FULL, hit ? (1u << src) : 0u);
+                collide |= (m >> lane) & 1u;
+            };
+
             // ---- obstacles of this time step --------------------------------------------------------------------
-            const float4 *s_cx4 = reinterpret_cast<const float4 *>(s_c);
-            const float4 *s_cy4 = reinterpret_cast<const float4 *>(s_c + p.cap_o);
-            const float4 *s_cr4 = reinterpret_cast<const float4 *>(s_c + 2 * p.cap_o);
-            const f32x2 nax = pack2(-acx, -acx), nay = pack2(-acy, -acy);
-            for (int ob = 0; ob < ocn; ob += 32) {
-                const int cnt = min(32, nobst - oc0 - ob);         // real obstacles in this block of 32 slots
-                // axis 0: centre line with bounding radii.  Three warp-broadcast LDS.128 bring four obstacles; packed
-                // FADD2/FFMA2 evaluate e = |dc|^2 - (rb + rcull)^2 for two of them per instruction and the sign bit
-                // of e is shifted into the hit word (bit 31-k <-> slot ob+k).
-                unsigned hits = 0;
-                if (!nocull) {
+            if (NOCULL) {
+                // full evaluation: every lane runs the complete test against every obstacle of the step
+                PolyRegs<VA> A;
+                A.load(sA, 32, lane);
+                for (int k = 0; k < min(ocn, nobst - oc0); k++) {
+                    PolyRegs<VB> B;
+                    B.load(s_ob, p.cap_o, k);
+                    const float sep = sat_polys<VA, VB>(A, B);
+                    if (active) {
+                        if (COUNT) n_axis++;
+                        if (sep < -tau) collide = true;
+                        else if (!(sep > tau)) push_work(p, q, ci, j, KIND_OBST, o0 + oc0 + k);
+                    }
+                    if (!noexit && (k & 31) == 31 && __all_sync(FULL, collide || !active)) break;
+                }
+            } else {
+                const float4 *s_cx4 = reinterpret_cast<const float4 *>(s_c);
+                const float4 *s_cy4 = reinterpret_cast<const float4 *>(s_c + p.cap_o);
+                const float4 *s_cr4 = reinterpret_cast<const float4 *>(s_c + 2 * p.cap_o);
+                const f32x2 nax = pack2(-acx, -acx), nay = pack2(-acy, -acy);
+                for (int ob = 0; ob < ocn; ob += 32) {
+                    // axis 0: centre line with bounding radii.  Three warp-broadcast LDS.128 bring four obstacles; packed
+                    // FADD2/FFMA2 evaluate e = |dc|^2 - (rb + rcull)^2 for two of them per instruction and the sign bit
+                    // of e is shifted into the hit word (bit 31-k <-> slot ob+k).
+                    unsigned hits = 0;
 #pragma unroll
                     for (int qd = 0; qd < 8; qd++) {
                         const float4 X = s_cx4[(ob >> 2) + qd], Y = s_cy4[(ob >> 2) + qd], R = s_cr4[(ob >> 2) + qd];
@@ -469,31 +591,22 @@ __global__ void __launch_bounds__(128, 6) k_check(const KParams p) {
                         hits = __funnelshift_l((unsigned)e23, hits, 1);
                         hits = __funnelshift_l((unsigned)(e23 >> 32), hits, 1);
                     }
-                } else {
-                    hits = ~((cnt >= 32) ? 0u : (FULL >> cnt));
-                }
-                if (!active || (collide && !noexit)) hits = 0;
-                if (COUNT && active) n_cull += cnt;
-                while (hits) {
-                    int k = __clz(hits);
-                    hits &= ~(0x80000000u >> k);
-                    float sep = sat_obstacle<VA, VB>(ax, ay, anx, any_, ac, s_ob, p.cap_o, ob + k);
-                    if (COUNT) n_axis++;
-                    if (sep < -tau) {
-                        collide = true;
-                        if (!noexit) hits = 0;
-                    } else if (!(sep > tau)) {
-                        push_work(p, q, ci, j, KIND_OBST, o0 + oc0 + ob + k);
+                    if (!active || (collide && !noexit)) hits = 0;
+                    if (COUNT && active) n_cull += min(32, nobst - oc0 - ob);
+                    push_hits(hits, ob, drain_obst);
+                    if (qn >= 32) {
+                        drain_obst();
+                        if (!noexit && __all_sync(FULL, collide || !active)) { qn = 0; break; }   // warp-wide early exit
                     }
                 }
-                if (!noexit && __all_sync(FULL, collide || !active)) break;   // warp-wide early exit
+                while (qn) drain_obst();
             }
 
             // ---- boundary segments of the free space at this time step -----------------------------------------
-            if (scn) {
+            if (scn && (noexit || !__all_sync(FULL, collide || !active))) {
                 // bounding box of the warp's 32 polygon centres and their largest radius: decides which 32-blocks of
                 // the (spatially sorted) segment range can matter for anyone in the warp
-                const bool blockcull = !nocull && nseg > 32;      // a single block cannot be skipped: no box work
+                const bool blockcull = !NOCULL && nseg > 32;      // a single block cannot be skipped: no box work
                 float wx0 = 0.f, wx1 = 0.f, wy0 = 0.f, wy1 = 0.f, wr = 0.f;
                 if (blockcull) {
                     wx0 = warp_min(active ? acx : BIG); wx1 = warp_max(active ? acx : -BIG);
@@ -550,36 +663,15 @@ __global__ void __launch_bounds__(128, 6) k_check(const KParams p) {
                             punc |= fabsf(dl) <= tau;
                         }
                         float tt = fmaf(-sl.y, acx - 0.5f * (sa.x + sa.z), sl.x * (acy - 0.5f * (sa.y + sa.w)));
-                        bool near = nocull ? (sl.w >= 0.f) : ((fabsf(dl) <= arr) & (fabsf(tt) <= sl.w + arr));
-                        if (near) hits |= 1u << k;
+                        bool near = NOCULL ? (sl.w >= 0.f) : ((fabsf(dl) <= arr) & (fabsf(tt) <= sl.w + arr));
+                        if (near) hits |= 0x80000000u >> k;
                     }
                     if (!active || (collide && !noexit)) hits = 0;
                     if (COUNT && active) n_cull += cnt;
-                    while (hits) {
-                        int k = __ffs(hits) - 1;
-                        hits &= hits - 1;
-                        float4 sa = s_sg[sb + k], sl = s_sg[p.cap_s + sb + k];
-                        float sep = -BIG, mn = BIG, mx = -BIG;
-#pragma unroll
-                        for (int e = 0; e < VA; e++) {
-                            float d0 = fmaf(anx[e], sa.x, fmaf(any_[e], sa.y, -ac[e]));
-                            float d1 = fmaf(anx[e], sa.z, fmaf(any_[e], sa.w, -ac[e]));
-                            sep = fmaxf(sep, fminf(d0, d1));
-                            float d = fmaf(sl.x, ax[e], fmaf(sl.y, ay[e], -sl.z));
-                            mn = fminf(mn, d);
-                            mx = fmaxf(mx, d);
-                        }
-                        sep = fmaxf(sep, fmaxf(mn, -mx));
-                        if (COUNT) n_axis++;
-                        if (sep < -tau) {
-                            collide = true;
-                            if (!noexit) hits = 0;
-                        } else if (!(sep > tau)) {
-                            push_work(p, q, ci, j, KIND_SEG, g0 + sc0 + sb + k);
-                        }
-                    }
-                    if (!noexit && __all_sync(FULL, collide || !active)) break;
+                    push_hits(hits, sb, drain_seg);
+                    if (qn >= 32) drain_seg();
                 }
+                while (qn) drain_seg();
             }
 
             // ---- fold this phase into the group state ----------------------------------------------------------
@@ -602,11 +694,11 @@ __global__ void __launch_bounds__(128, 6) k_check(const KParams p) {
         if (nphase > 1) __syncthreads();      // everyone is done with the tile before the next bulk copy overwrites it
     }
     if (COUNT) {
-        n_cull = __reduce_add_sync(FULL, (unsigned)n_cull) ;
-        unsigned a = __reduce_add_sync(FULL, (unsigned)n_axis);
+        n_cull = __reduce_add_sync(FULL, n_cull);
+        n_axis = __reduce_add_sync(FULL, n_axis);
         if (lane == 0) {
-            atomicAdd(&p.cnt->cull_tests, n_cull);
-            atomicAdd(&p.cnt->axis_tests, (unsigned long long)a);
+            atomicAdd(&p.cnt->cull_tests, (unsigned long long)n_cull);
+            atomicAdd(&p.cnt->axis_tests, (unsigned long long)n_axis);
         }
     }
 }
@@ -1175,14 +1267,16 @@ static KParams make_params(mpc_ctx *ctx) {
 
 template <int VA, int VB>
 static cudaError_t launch_check_vb(mpc_ctx *ctx, const KParams &p) {
-    auto kern = (ctx->mode & MPC_MODE_COUNT_WORK) ? k_check<VA, VB, true> : k_check<VA, VB, false>;
-    const int key = VA * 1000 + VB * 10 + ((ctx->mode & MPC_MODE_COUNT_WORK) ? 1 : 0);
+    const bool count = ctx->mode & MPC_MODE_COUNT_WORK, nocull = ctx->mode & MPC_MODE_NO_CULL;
+    auto kern = nocull ? (count ? k_check<VA, VB, true, true> : k_check<VA, VB, false, true>)
+                       : (count ? k_check<VA, VB, true, false> : k_check<VA, VB, false, false>);
+    const int key = VA * 1000 + VB * 10 + (count ? 1 : 0) + (nocull ? 2 : 0);
     if (ctx->smem > 48 * 1024 && ctx->smem_attr[key] < ctx->smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem);
         if (e != cudaSuccess) return e;
         ctx->smem_attr[key] = ctx->smem;
     }
-    kern<<<ctx->ctas, ctx->threads, ctx->smem, ctx->stream>>>(p);
+    kern<<<ctx->ctas, K_THREADS, ctx->smem, ctx->stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -1235,16 +1329,18 @@ extern "C" int mpc_prepare_query(mpc_ctx *ctx, int B, const mpc_query_desc *quer
     for (int i = 0; i < ncand; i++)
         if (cand_idx[i] < 0 || cand_idx[i] >= ctx->P) return fail(ctx, MPC_E_ARG, "cand_idx[%d]=%d outside the library", i, cand_idx[i]);
     const int sms = ctx->prop.multiProcessorCount;
-    ctx->threads = 128;
-    const int nwarps = ctx->threads / 32;
-    int gpc = (int)((total_groups + (long long)sms * 6 - 1) / ((long long)sms * 6));
+    ctx->threads = K_THREADS;
+    const int nwarps = K_THREADS / 32;
+    // groups (of 32 candidates) per CTA: enough CTAs for ~2 waves of 4 CTAs per SM, whole rounds of the CTA's warps
+    int gpc = (int)((total_groups + (long long)sms * 8 - 1) / ((long long)sms * 8));
     gpc = std::max(1, std::min(gpc, GPC_MAX));
-    if (gpc > 1) gpc = std::min(GPC_MAX, (gpc + nwarps - 1) / nwarps * nwarps);   // whole rounds of the CTA's warps
+    if (gpc > nwarps / 2) gpc = std::min(GPC_MAX, (gpc + nwarps - 1) / nwarps * nwarps);
     ctx->gpc = gpc;
-    const int F = ob_fields(ctx->VB);
+    const int F = ob_fields(ctx->VB), FA = ob_fields(ctx->VA);
     ctx->cap_o = std::max(32, std::min((ctx->max_obst_step + 31) / 32 * 32, ctx->VB == 4 ? 320 : 160));
     ctx->cap_s = std::max(32, std::min((ctx->max_seg_step + 31) / 32 * 32, 512));
-    ctx->smem = 16 + 3 * GPC_MAX * 4 + (size_t)ctx->cap_o * (F * 16 + 12) + (size_t)ctx->cap_s * 32;
+    ctx->smem = 16 + 3 * GPC_MAX * 4 + (size_t)nwarps * QCAP * 4 + (size_t)nwarps * FA * 32 * 16 +
+                (size_t)ctx->cap_o * (F * 16 + 12) + (size_t)ctx->cap_s * 32;
     // pack: QDev[B], cta_off[B+1] (one copy), explicit candidates (second copy, only when present)
     size_t bytes_q = sizeof(QDev) * (size_t)std::max(B, 1), bytes_c = sizeof(int) * (size_t)(B + 1), bytes_i = sizeof(int) * (size_t)ncand;
     CU(ensure_pinned(ctx, bytes_q + bytes_c + bytes_i + 64));
