@@ -14,11 +14,31 @@ import numpy as np
 
 
 class _Ring:
+    """closed coordinate sequence; built from a list of points or an [n,2] array (coords are materialised lazily)"""
+
     def __init__(self, coords):
-        c = [(float(p[0]), float(p[1])) for p in coords]
-        if c and c[0] != c[-1]:
-            c.append(c[0])
-        self.coords = c
+        self._arr = None
+        self._coords = None
+        if isinstance(coords, np.ndarray):
+            a = np.asarray(coords, dtype=np.float64).reshape(-1, 2)
+            if len(a) and (a[0, 0] != a[-1, 0] or a[0, 1] != a[-1, 1]):
+                a = np.concatenate([a, a[:1]])
+            self._arr = a
+        else:
+            c = [(float(p[0]), float(p[1])) for p in coords]
+            if c and c[0] != c[-1]:
+                c.append(c[0])
+            self._coords = c
+
+    @property
+    def coords(self):
+        if self._coords is None:
+            self._coords = [(float(x), float(y)) for x, y in self._arr]
+        return self._coords
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._arr if self._arr is not None else np.asarray(self._coords, dtype=np.float64).reshape(-1, 2)
+        return a if dtype is None else a.astype(dtype)
 
     def distance(self, point):
         """euclidean distance from a Point to this ring (shapely LinearRing.distance)"""
@@ -78,13 +98,14 @@ class Polygon:
     geom_type = 'Polygon'
 
     def __init__(self, shell=None, holes=None):
-        shell = [] if shell is None else list(shell)
-        self.exterior = _Ring(shell)
+        if shell is None:
+            shell = []
+        self.exterior = _Ring(shell if isinstance(shell, np.ndarray) else list(shell))
         self.interiors = [_Ring(h) for h in (holes or [])]
 
     @property
     def is_empty(self):
-        return len(self.exterior.coords) < 4
+        return len(np.asarray(self.exterior)) < 4
 
     def contains(self, other):
         """only Point arguments are decided on the host (goal test); polygons go through the GPU checker"""

@@ -5,6 +5,21 @@ import numpy as np
 from ..geometry import polygon_vertices
 
 
+def _fast_vertices(geom):
+    """open vertex array of a polygon-like object (closing vertex and repeated vertices dropped)"""
+    c = geom.exterior if hasattr(geom, 'exterior') else geom
+    c = c if hasattr(c, '__array__') else c.coords
+    v = np.asarray(c, dtype=np.float64).reshape(-1, 2)
+    if len(v) > 1 and v[0, 0] == v[-1, 0] and v[0, 1] == v[-1, 1]:
+        v = v[:-1]
+    if len(v) > 1:
+        keep = np.ones(len(v), bool)
+        keep[1:] = (v[1:, 0] != v[:-1, 0]) | (v[1:, 1] != v[:-1, 1])
+        if not keep.all():
+            v = v[keep]
+    return v
+
+
 class MotionPrimitive:
     """one motion primitive: reference trajectory, inputs, duration, successors and occupancy sets"""
 
@@ -43,11 +58,24 @@ class ManeuverAutomaton:
     def __getstate__(self):
         d = dict(self.__dict__)
         d.pop('_layouts', None)
+        d.pop('_stacks', None)
         return d
 
     def __setstate__(self, d):
         self.__dict__.update(d)
         self._layouts = {}
+
+    def bucket_stacks(self, bucket):
+        """reference trajectories of a velocity bucket stacked by length: [(positions in the bucket, [m, 4, L])];
+        lets a planner expand all children of a node with one batched product instead of one per child"""
+        cache = self.__dict__.setdefault('_stacks', {})
+        if bucket not in cache:
+            by_len = {}
+            for k, i in enumerate(self.vel_dic[bucket]):
+                by_len.setdefault(self.primitives[i].x.shape[1], []).append(k)
+            cache[bucket] = [(np.array(ks), np.stack([self.primitives[self.vel_dic[bucket][k]].x for k in ks]))
+                             for _, ks in sorted(by_len.items())]
+        return cache[bucket]
 
     # ------------------------------------------------------------------------------------------------------------
     def is_timepoint(self):
@@ -72,11 +100,12 @@ class ManeuverAutomaton:
         per_prim, slot_keys, vmax = [], set(), 3
         for p in self.primitives:
             seen, items = {}, []
-            for o in (p.occ or []):
+            arr = getattr(p, '_occ_verts', None)
+            for k, o in enumerate(p.occ or []):
                 t = int((o['time'] if timepoint else o['starttime']) / time_step)
                 rank = seen.get(t, 0)
                 seen[t] = rank + 1
-                v = polygon_vertices(o['space'])
+                v = arr[k] if arr is not None else _fast_vertices(o['space'])
                 vmax = max(vmax, len(v))
                 items.append(((t, rank), v))
                 slot_keys.add((t, rank))

@@ -72,13 +72,14 @@ def _simulate(plan, param, dt=DT):
 
 
 def _occupancy(x, car, dt=DT):
-    occ = []
-    for i in range(x.shape[1]):
-        c, s = np.cos(x[3, i]), np.sin(x[3, i])
-        # shapely affine_transform(car, [cos, -sin, sin, cos, x, y]): a*x + b*y + xoff per point
-        pts = [(c * px + (-s) * py + x[0, i], s * px + c * py + x[1, i]) for px, py in car]
-        occ.append({'space': Polygon(pts), 'time': dt * i})
-    return occ
+    """car outline at every state: shapely affine_transform(car, [cos, -sin, sin, cos, x, y]) = a*x + b*y + xoff per
+    point, evaluated for all states at once (same arithmetic, element by element)"""
+    car = np.asarray(car)
+    c, s = np.cos(x[3])[:, None], np.sin(x[3])[:, None]
+    px = c * car[:, 0] + (-s) * car[:, 1] + x[0][:, None]
+    py = s * car[:, 0] + c * car[:, 1] + x[1][:, None]
+    verts = np.stack([px, py], axis=-1)                       # [n, 4, 2]
+    return [{'space': Polygon(verts[i]), 'time': dt * i} for i in range(x.shape[1])], verts
 
 
 def create_maneuver_automaton(param=None, states=None, plan=None):
@@ -87,8 +88,12 @@ def create_maneuver_automaton(param=None, states=None, plan=None):
     plan = plan if plan is not None else _plan(param)
     states = states if states is not None else _simulate(plan, param)
     car = car_outline(param)
-    prims = [MotionPrimitive(x, np.array([acc, steer]), tf, occupancy=_occupancy(x, car))
-             for (v, acc, steer, tf), x in zip(plan, states)]
+    prims = []
+    for (v, acc, steer, tf), x in zip(plan, states):
+        occ, verts = _occupancy(x, car)
+        p = MotionPrimitive(x, np.array([acc, steer]), tf, occupancy=occ)
+        p._occ_verts = verts            # the same vertices as an array: lets device_layout() skip 150 k Python objects
+        prims.append(p)
     return ManeuverAutomaton(prims)
 
 

@@ -22,13 +22,28 @@ from ..maneuverAutomaton.Controller import FeedbackController
 
 
 class Node:
-    """search node: sequence of primitive indices, rear-axle trajectory 4 x (10 k + 1), accumulated cost"""
+    """search node: sequence of primitive indices, rear-axle trajectory 4 x (10 k + 1), accumulated cost.
+    Children created by the batched expansion keep (parent, own segment) and build ``x`` on first use -- only nodes
+    that are actually popped ever need the full trajectory."""
+    __slots__ = ('primitives', '_x', 'cost', 'collides', '_parent', '_seg')
 
-    def __init__(self, primitives, x, cost, collides=None):
+    def __init__(self, primitives, x, cost, collides=None, parent=None, seg=None):
         self.primitives = primitives
-        self.x = x
+        self._x = x
         self.cost = cost
         self.collides = collides          # geometry bit of the last primitive (None: not evaluated yet)
+        self._parent, self._seg = parent, seg
+
+    @property
+    def x(self):
+        if self._x is None:
+            self._x = np.concatenate((self._parent.x[:, :-1], self._seg), axis=1)
+            self._parent = None
+        return self._x
+
+    @x.setter
+    def x(self, value):
+        self._x = value
 
 
 def _rotation(phi):
@@ -121,17 +136,42 @@ def transform_trajectory(x, param):
 
 
 def _children(checker, node, MA, bucket, ref_traj, fixed, param, scenes):
-    """expand `node` by every primitive of velocity bucket `bucket`; one device query decides all of them"""
-    ind = node.x.shape[1] - 1
+    """expand `node` by every primitive of velocity bucket `bucket`: one device query decides all of them, one batched
+    product builds all child trajectories.  Same arithmetic per child as expand_node (reference :192-214)."""
+    x = node.x
+    ind = x.shape[1] - 1
     cand = MA.vel_dic[bucket]
     if not cand:
         return []
     if _time_exceeded(ind, param['goal']):
         bits = np.ones(len(cand), bool)           # the reference rejects these before looking at geometry (:99-109)
     else:
-        bits = checker.bucket_collides(node.x[0, -1], node.x[1, -1], node.x[3, -1], ind, param['steps'], bucket, scenes)
-    T = _rotation(node.x[3, -1])
-    return [expand_node(node, MA.primitives[i], i, ref_traj, fixed, T, bool(b)) for i, b in zip(cand, bits)]
+        bits = checker.bucket_collides(x[0, -1], x[1, -1], x[3, -1], ind, param['steps'], bucket, scenes)
+    T = _rotation(x[3, -1])
+    off = np.array([[x[0, -1]], [x[1, -1]], [0], [x[3, -1]]])
+    costs = np.empty(len(cand))
+    segs = [None] * len(cand)
+    for loc, PX in MA.bucket_stacks(bucket):
+        X = T @ PX + off                                           # [m, 4, L]
+        last = min(ind + PX.shape[2], ref_traj.shape[1])
+        if last > ind:
+            d = ref_traj[0:2, ind:last][None] - X[:, 0:2, :last - ind]
+            # the reference sums `(ref_traj[0:2, index] - x[0:2, index])**2`, whose fancy-indexed operands are
+            # Fortran-ordered: numpy adds x0, y0, x1, y1, ... -- reproduce that order so costs match to the last bit
+            sq = np.ascontiguousarray(np.swapaxes(d ** 2, 1, 2))
+            costs[loc] = node.cost + sq.reshape(len(loc), -1).sum(axis=1)
+        else:
+            costs[loc] = node.cost + 0.0
+        for k, i in enumerate(loc):
+            segs[i] = X[k]
+    depth = len(node.primitives) + 1
+    out = []
+    for k, i in enumerate(cand):
+        cost = costs[k]
+        if depth <= len(fixed) and i != fixed[depth - 1]:
+            cost = cost + 1000
+        out.append(Node(node.primitives + [i], None, cost, bool(bits[k]), node, segs[k]))
+    return out
 
 
 def lowLevelPlannerManeuverAutomaton(scenario, planning_problem, param, space_all, ref_traj, MA, search_horizon=2,

@@ -138,3 +138,21 @@ def test_standalone_planner_cpu_on_zam_zip(MA):
     flags, _ = CC.collision_flags(scenario, x, param, engine=OracleBackend())
     assert not flags.any()
     assert goals[0]['space'].contains(LL.Point(x[0, -1], x[1, -1]))
+
+
+def test_batched_expansion_equals_per_child_expand_node(MA):
+    """the vectorised child construction reproduces expand_node (reference :192-214) bit for bit"""
+    param, space, ref = corridor_problem(blocked=True)
+    be = OracleBackend()
+    LL._CACHE.clear()
+    chk = LL._checker_for(MA, 0.1, space, True, be)
+    x = np.array([[0.3 - 1.15], [0.2], [10.0], [0.07]])
+    root = LL.Node([], x, 1.25)
+    for bucket, fixed in ((int(MA._bucket(10.0)), []), (int(MA._bucket(0.4)), [3]), (int(MA._bucket(29.6)), [])):
+        kids = LL._children(chk, root, MA, bucket, ref, fixed, param, (0,))
+        T = LL._rotation(x[3, -1])
+        assert len(kids) == len(MA.vel_dic[bucket])
+        for k, i in zip(kids, MA.vel_dic[bucket]):
+            one = LL.expand_node(root, MA.primitives[i], i, ref, fixed, T)
+            assert k.primitives == one.primitives and k.cost == one.cost
+            assert np.array_equal(k.x, one.x)
