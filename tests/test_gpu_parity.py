@@ -251,3 +251,21 @@ def test_error_behaviour(eng):
     with pytest.raises(MpcError):
         CollisionEngine(99)
     e2.close()
+
+
+def test_repeatability_under_load(eng):
+    """the warp queues, shared-memory polygon records and atomics must not make results depend on scheduling:
+    the same mid-size batch 25 times, in both cull modes, must give the identical mask every time"""
+    lib, sc, org, q = W.c4_problem(P=1024, slots=24, T=20, nqueries=6)
+    stage(eng, lib, sc, org)
+    want, _ = orc.Problem(lib, sc).check(q, None, orc.MODE_NO_EARLY_EXIT, inner_parallel=True)
+    for mode in (MODE_PLANNER, MODE_NO_EARLY_EXIT, MODE_NO_CULL):
+        for _ in range(25 if mode != MODE_NO_CULL else 3):
+            got, _ = eng.query(q, None, mode)
+            assert np.array_equal(got, want)
+    lib, sc, org, q = W.adversarial_problem(77, P=320, J=7, max_obst=90, nqueries=5)
+    stage(eng, lib, sc, org)
+    want, _ = orc.Problem(lib, sc).check(q, None, orc.MODE_NO_EARLY_EXIT)
+    for _ in range(25):
+        got, _ = eng.query(q, None, MODE_PLANNER)
+        assert np.array_equal(got, want)

@@ -156,3 +156,61 @@ def test_batched_expansion_equals_per_child_expand_node(MA):
             one = LL.expand_node(root, MA.primitives[i], i, ref, fixed, T)
             assert k.primitives == one.primitives and k.cost == one.cost
             assert np.array_equal(k.x, one.x)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SCENARIOS), reason="reference scenarios not mounted (build container only)")
+def test_batch_harness_writes_reference_csv_format(MA, tmp_path):
+    """evaluation/runAllScenarios.py mirror: CSV rows `file, comp_time, collision, tags, final_time` that the
+    reference's evaluationScript.py (evaluation_matrics :7-22) can aggregate"""
+    from motionplanner_b200.auxiliary import collisionChecker as CC
+    from motionplanner_b200.evaluation.runAllScenarios import run_all
+    validator = lambda sc, x, prm: not CC.collision_flags(sc, x, prm, engine=OracleBackend())[0].any()
+    out, data = run_all(REF_SCENARIOS, str(tmp_path), max_nodes=20000, files=['ZAM_Zip-1_19_T-1.xml', 'USA_Lanker-1_8_T-1.xml'],
+                        backend=OracleBackend(), validator=validator)
+    rows = [l.strip().split(',') for l in open(out)]
+    assert len(rows) == 2 and all(len(r) == 5 for r in rows)
+    assert rows[0][0] == 'ZAM_Zip-1_19_T-1.xml' and rows[0][2] == 'no collision' and float(rows[0][4]) == 8.5
+    assert rows[0][1].replace('.', '', 1).isdigit()            # the test evaluationScript.py uses for "solved"
+    assert rows[1][1] == 'failed'
+
+
+def test_interval_occupancies_use_two_consecutive_free_spaces():
+    """AROC-style automaton (time-interval occupancies): the reference intersects consecutive free spaces
+    (src/lowLevelPlannerManeuverAutomaton.py:25-30); here the occupancy is tested against both steps.  Checked
+    against exact containment in both polygons, including the shortened horizon (len(space) - 1)."""
+    from motionplanner_b200.maneuverAutomaton.ManeuverAutomaton import ManeuverAutomaton, MotionPrimitive
+    rng = np.random.default_rng(3)
+    prims = []
+    for i in range(40):
+        x = np.zeros((4, 11))
+        x[2] = 2.0 if i < 30 else 2.4                  # the constructor needs at least two velocity buckets
+        x[0] = np.linspace(0, 2.0, 11)
+        occ = []
+        for k in range(10):
+            cx, cy = 0.2 * k + rng.uniform(-0.3, 0.3), rng.uniform(-1.5, 1.5)
+            occ.append({'space': Polygon([(cx - 1, cy - 0.5), (cx + 1, cy - 0.5), (cx + 1, cy + 0.5), (cx - 1, cy + 0.5)]),
+                        'starttime': float('%.1f' % (0.1 * k)), 'endtime': float('%.1f' % (0.1 * k + 0.1))})
+        prims.append(MotionPrimitive(x, np.zeros((2, 10)), 1.0, occupancy=occ))
+    MA2 = ManeuverAutomaton(prims)
+    assert not MA2.is_timepoint()
+    # free space shrinks and shifts over time
+    space = [Polygon([(-2 + 0.1 * t, -2.2 + 0.05 * t), (6, -2.2 + 0.05 * t), (6, 2.4 - 0.08 * t), (-2 + 0.1 * t, 2.4 - 0.08 * t)])
+             for t in range(9)]
+    be = OracleBackend()
+    LL._CACHE.clear()
+    chk = LL._checker_for(MA2, 0.1, space, False, be)
+    for t0 in (0, 3):
+        bits = chk.bucket_collides(0.5, 0.1, 0.05, t0, 20, int(MA2._bucket(2.0)), (0, 1))
+        c, s = np.cos(0.05), np.sin(0.05)
+        for i, p in enumerate(prims[:30]):
+            collide = False
+            for o in p.occ:
+                t = t0 + int(o['starttime'] / 0.1)
+                if t > 20 or t >= len(space) - 1:              # reference guards with the intersected list
+                    continue
+                A = ex.affine_transform(list(o['space'].exterior.coords[:-1]), c, s, 0.5, 0.1)
+                for sp in (space[t], space[t + 1]):
+                    if not ex.region_contains_convex([list(sp.exterior.coords)], A):
+                        collide = True
+            assert bool(bits[i]) == collide, (t0, i)
+        assert 0 < bits.sum() < len(bits)
