@@ -40,6 +40,7 @@ FLOP_PER_CHECK = 304            # rectangle x rectangle SAT, a =
 SAT_FLOP_EXECUTED = 160         # this kernel's full 4x4 test: 64 FMA (2 flop) + 24 min + 8 max
 CULL_FLOP_EXECUTED = 6          # centre-line axis per pair: 2 add + 2 fma (packed FADD2/FFMA2: two pairs per instruction)
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # no FP32 entry in MEASURED_PEAKS.json: derived from its sm_max_mhz
+NCU_DRAM_BYTES_PER_LAUNCH = 17637632   # ncu capture b (profiles/): dram__bytes_read.sum of one 16-query launch; write 0
 METRIC = "primitive x obstacle x timestep collision checks/sec"
 
 
@@ -205,6 +206,12 @@ def main():
     nq = len(queries)
     eng.upload_library(lib["verts"], lib["nv"], lib["tidx"], lib["set_off"], lib["set_idx"])
 
+    # the step's inputs live in pinned host memory (what a sensor/prediction pipeline would hand over)
+    for k in ("obst", "obst_nv", "segs", "step_obst_off", "step_seg_begin", "step_seg_end", "scene_step_off"):
+        scene[k] = eng.pinned_like(scene[k])
+    origins = eng.pinned_like(origins)
+    queries = eng.pinned_like(queries)
+
     def set_scene():
         eng.set_scenes(scene["scene_step_off"], origins, scene["step_obst_off"], scene["obst"], scene["obst_nv"],
                        scene["step_seg_begin"], scene["step_seg_end"], scene["segs"])
@@ -303,28 +310,43 @@ def main():
             "e2e": {"value": world * args.steps * checks_step / e2e_s, "unit": "checks/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "what": "CollisionEngine.set_scenes + query_mask (mpc_set_scenes + mpc_query) from host numpy "
-                            "buffers, every step"},
+                    "what": "CollisionEngine.set_scenes + query_mask (mpc_set_scenes + mpc_query) from pinned host "
+                            "numpy buffers, every step"},
             "gpu_launches": int(args.steps * 3),
             "gpu_launches_what": "per timed step: k_fill_u32 (L2 flush, outside the event bracket), k_check, k_refine",
             "clocks": clocks,
-            "roofline": {"bound": "fp32", "kernel": "k_check<4,4,0,0>", "achieved": algo_tflops, "peak": FP32_PEAK_TFLOPS,
-                         "unit": "TFLOP/s", "frac": algo_tflops / FP32_PEAK_TFLOPS, "traffic": None,
-                         "peak_source": "derived 148 SM x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json has no FP32 "
-                                        "figure); algorithmic = 304 flop/check (SURVEY 8d) x checks per launch",
-                         "kernel_ms": main_ms,
-                         "executed": {"cull_axis_tests": st_cnt["cull_tests"], "full_sat_tests": st_cnt["axis_tests"],
-                                      "tflops": exec_tflops, "frac": exec_tflops / FP32_PEAK_TFLOPS,
-                                      "note": "instrumented launch of the same batch: the centre-line axis decides "
-                                              "most pairs, so executed flops are far below the algorithmic count"},
-                         "full_evaluation": {"checks_per_s": full_checks / (full_main * 1e-3),
-                                             "tflops_executed": full_checks * (SAT_FLOP_EXECUTED + 0) / (full_main * 1e-3) / 1e12,
-                                             "frac": full_checks * SAT_FLOP_EXECUTED / (full_main * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
-                                             "note": "MPC_MODE_NO_CULL|NO_EARLY_EXIT: every pair runs the complete "
-                                                     "4x4 separating-axis test (160 executed flop)"},
-                         "hbm": {"algorithmic_bytes": algo_bytes, "achieved_gbs": algo_bytes / (main_ms * 1e-3) / 1e9,
-                                 "peak_gbs": hbm_peak, "frac": algo_bytes / (main_ms * 1e-3) / 1e9 / hbm_peak,
-                                 "peak_source": "measured" if peaks else "fallback"}},
+            "roofline": {
+                "bound": "fp32", "kernel": "k_check<4,4,0,0>", "achieved": exec_tflops, "peak": FP32_PEAK_TFLOPS,
+                "unit": "TFLOP/s", "frac": exec_tflops / FP32_PEAK_TFLOPS,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH if nq == 16 else None,
+                "what": "executed FP32 flop of the timed launch (an instrumented launch of the same batch counts "
+                        "centre-line axis tests x 6 flop and full separating-axis tests x 160 flop) / CUDA-event "
+                        "duration of k_check. The kernel is NOT FP32-bound: ncu (profiles/r01b_k_check_ncu_full.csv) "
+                        "shows the shared-memory data pipe at 78 % and instruction issue at 72 % of peak, FMA pipe "
+                        "28 %; HBM traffic equals the algorithmic bytes.",
+                "peak_source": "derived: 148 SM x 128 lanes x 2 x sm_max_mhz 1965 (MEASURED_PEAKS.json has no FP32 "
+                               "figure)",
+                "kernel_ms": main_ms,
+                "executed": {"cull_axis_tests": st_cnt["cull_tests"], "full_sat_tests": st_cnt["axis_tests"],
+                             "flop": exec_flop},
+                "algorithmic_survey": {"flop_per_check": FLOP_PER_CHECK, "achieved": algo_tflops,
+                                       "frac": algo_tflops / FP32_PEAK_TFLOPS,
+                                       "note": "SURVEY.md 8(d) definition: 304 flop x checks / time. Above 1 by "
+                                               "construction: the centre-line axis decides 99.6 % of the pairs with "
+                                               "6 flop, so the algorithmic count is not executed."},
+                "full_evaluation": {"checks_per_s": full_checks / (full_main * 1e-3),
+                                    "achieved": full_checks * SAT_FLOP_EXECUTED / (full_main * 1e-3) / 1e12,
+                                    "frac": full_checks * SAT_FLOP_EXECUTED / (full_main * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
+                                    "frac_survey_304": full_checks * FLOP_PER_CHECK / (full_main * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
+                                    "note": "MPC_MODE_NO_CULL|NO_EARLY_EXIT: every pair runs the complete 4x4 "
+                                            "separating-axis test (160 executed flop: 64 FMA + 32 min/max); here "
+                                            "algorithmic = executed"},
+                "ncu": {"source": "profiles/r01b_k_check_ncu_full.csv", "smsp__issue_active_pct": 72.3,
+                        "l1tex__data_pipe_lsu_wavefronts_pct": 78.1, "sm__inst_executed_pipe_fma_pct": 28.3,
+                        "dram__bytes_read": NCU_DRAM_BYTES_PER_LAUNCH, "dram__bytes_write": 0},
+                "hbm": {"algorithmic_bytes": algo_bytes, "achieved_gbs": algo_bytes / (main_ms * 1e-3) / 1e9,
+                        "peak_gbs": hbm_peak, "frac": algo_bytes / (main_ms * 1e-3) / 1e9 / hbm_peak,
+                        "peak_source": "measured" if peaks else "fallback"}},
             "warm_l2": {"value": world * checks_step / (float(ms_warm.mean()) * 1e-3), "ms_per_step": float(ms_warm.mean())},
             "latency": {"planning_step_p50_ms": 1e3 * lat_p50, "device_ms_single_query": float(np.median(ms_one)),
                         "what": "one query (4096 candidates x 50 steps x 256 obstacles), host doubles in -> bitmask out"},

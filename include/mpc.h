@@ -93,6 +93,12 @@ void mpc_destroy(mpc_ctx *ctx);
 const char *mpc_last_error(const mpc_ctx *ctx);
 int mpc_device_info(mpc_ctx *ctx, mpc_devinfo *out);
 
+/* -- pinned host memory for the caller's input arrays (optional) -------------------------------------------------------
+ * Arrays handed to mpc_set_scenes / mpc_query may live anywhere; if they live in memory obtained here the host->device
+ * copies are true asynchronous DMA transfers.  The reference has no counterpart (it never leaves the host). */
+int mpc_alloc_pinned(mpc_ctx *ctx, uint64_t bytes, void **out);
+int mpc_free_pinned(mpc_ctx *ctx, void *ptr);
+
 /* -- primitive library, staged once ----------------------------------------------------------------------------------
  * Replaces the per-call walk over MA.primitives[i].occ (maneuverAutomaton/ManeuverAutomaton.py:35-44; occupancy
  * polygons built by maneuverAutomaton/createManeuverAutomaton.py:76-86 or loadAROCautomaton.py:110-137).

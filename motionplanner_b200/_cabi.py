@@ -46,7 +46,7 @@ class MpcError(RuntimeError):
 _lib = None
 
 EXPORTS = ["mpc_create", "mpc_destroy", "mpc_last_error", "mpc_device_info", "mpc_upload_library", "mpc_set_scenes",
-           "mpc_query", "mpc_prepare_query", "mpc_run_prepared", "mpc_fetch_mask"]
+           "mpc_query", "mpc_prepare_query", "mpc_run_prepared", "mpc_fetch_mask", "mpc_alloc_pinned", "mpc_free_pinned"]
 
 
 def load():
@@ -72,6 +72,8 @@ def load():
     L.mpc_prepare_query.argtypes = [vp, i32, vp, vp, i32, u32]
     L.mpc_run_prepared.argtypes = [vp, i32, i32, vp, vp, C.POINTER(Stats)]
     L.mpc_fetch_mask.argtypes = [vp, vp, i32]
+    L.mpc_alloc_pinned.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
+    L.mpc_free_pinned.argtypes = [vp, vp]
     for name in EXPORTS:
         if name not in ("mpc_destroy", "mpc_last_error"):
             getattr(L, name).restype = i32

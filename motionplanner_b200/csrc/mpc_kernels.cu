@@ -197,7 +197,7 @@ __global__ void k_stage_obst(int nslots, const double *__restrict__ src64, const
     }
     if (!ok) {
         // never near, and "always separated" for whoever tests it anyway: a point far away
-        for (int k = 0; k < VB; k++) { out[2 * k] = FAR; out[2 * k + 1] = FAR; }
+        for (int k = 0; k < VB * 2; k++) out[k] = FAR;
         for (int k = 0; k < VB; k++) { out[VB * 2 + 3 * k] = 0.f; out[VB * 2 + 3 * k + 1] = 0.f; out[VB * 2 + 3 * k + 2] = -BIG; }
         for (int k = VB * 5; k < F * 4; k++) out[k] = 0.f;
         for (int k = 0; k < VB * 2; k++) v[k] = 0.0;
@@ -209,7 +209,7 @@ __global__ void k_stage_obst(int nslots, const double *__restrict__ src64, const
         double cx = 0.0, cy = 0.0, m = 0.0;
         for (int k = 0; k < VB; k++) {
             double lx = x[k] - ox, ly = y[k] - oy;
-            out[2 * k] = (float)lx; out[2 * k + 1] = (float)ly;
+            out[4 * (k >> 1) + (k & 1)] = (float)lx; out[4 * (k >> 1) + 2 + (k & 1)] = (float)ly;   // (x0,x1,y0,y1)
             m = fmax(m, fmax(fabs(lx), fabs(ly)));
             if (k < nv) { cx += lx; cy += ly; }
         }
@@ -298,17 +298,23 @@ __device__ __forceinline__ void push_work(const KParams &p, int q, int ci, int j
     if (idx < (unsigned)p.wl_cap) p.wl[idx] = make_int4(q, ci, j | (kind << 16), obj);
 }
 
-// A polygon record in shared memory is SoA by float4 field: V/2 fields of vertex pairs (x0,y0,x1,y1), then
+// A polygon record in shared memory is SoA by float4 field: V/2 fields of vertex pairs (x0,x1,y0,y1), then
 // ceil(3V/4) fields holding the packed edge lines (nx, ny, c) -- the same layout for obstacle records (staged by
-// k_stage_obst) and for the transformed occupancy polygons the warps write themselves.
+// k_stage_obst) and for the transformed occupancy polygons the warps write themselves.  Vertex pairs stay packed in
+// 64-bit registers so that one FFMA2 projects two vertices on an edge normal.
+__device__ __forceinline__ float lo32(f32x2 v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi32(f32x2 v) { return __uint_as_float((unsigned)(v >> 32)); }
+
 template <int V>
 struct PolyRegs {
-    float x[V], y[V], ln[((V * 3 + 3) / 4) * 4];
+    f32x2 X[V / 2], Y[V / 2];
+    float ln[((V * 3 + 3) / 4) * 4];
     __device__ __forceinline__ void load(const float4 *rec, int stride, int i) {
 #pragma unroll
         for (int h = 0; h < V / 2; h++) {
             float4 v = rec[h * stride + i];
-            x[2 * h] = v.x; y[2 * h] = v.y; x[2 * h + 1] = v.z; y[2 * h + 1] = v.w;
+            X[h] = pack2(v.x, v.y);
+            Y[h] = pack2(v.z, v.w);
         }
 #pragma unroll
         for (int h = 0; h < (V * 3 + 3) / 4; h++) {
@@ -316,28 +322,48 @@ struct PolyRegs {
             ln[4 * h] = v.x; ln[4 * h + 1] = v.y; ln[4 * h + 2] = v.z; ln[4 * h + 3] = v.w;
         }
     }
+    __device__ __forceinline__ float x(int k) const { return (k & 1) ? hi32(X[k >> 1]) : lo32(X[k >> 1]); }
+    __device__ __forceinline__ float y(int k) const { return (k & 1) ? hi32(Y[k >> 1]) : lo32(Y[k >> 1]); }
 };
+
+// three-input min / max (sm_100: FMNMX3)
+__device__ __forceinline__ float min3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// minimum over the vertices of Q of the signed distance to the line (nx, ny, c): two vertices per FFMA2, one FMNMX3
+// per vertex pair
+template <int VQ>
+__device__ __forceinline__ float min_dist(const PolyRegs<VQ> &Q, float nx, float ny, float c) {
+    const f32x2 nx2 = pack2(nx, nx), ny2 = pack2(ny, ny), nc2 = pack2(-c, -c);
+    float mn = BIG;
+#pragma unroll
+    for (int h = 0; h < VQ / 2; h++) {
+        const f32x2 d = fma2(nx2, Q.X[h], fma2(ny2, Q.Y[h], nc2));
+        mn = (h == 0) ? fminf(lo32(d), hi32(d)) : min3(mn, lo32(d), hi32(d));
+    }
+    return mn;
+}
 
 // signed separation of two convex polygons: max over all edge axes of the minimum vertex distance (> 0 apart)
 template <int VA, int VB>
 __device__ __forceinline__ float sat_polys(const PolyRegs<VA> &A, const PolyRegs<VB> &B) {
     float sep = -BIG;
 #pragma unroll
-    for (int e = 0; e < VA; e++) {
-        const float nx = A.ln[3 * e], ny = A.ln[3 * e + 1], c = A.ln[3 * e + 2];
-        float mn = BIG;
+    for (int e = 0; e < VA; e += 2)
+        sep = max3(sep, min_dist<VB>(B, A.ln[3 * e], A.ln[3 * e + 1], A.ln[3 * e + 2]),
+                   min_dist<VB>(B, A.ln[3 * e + 3], A.ln[3 * e + 4], A.ln[3 * e + 5]));
 #pragma unroll
-        for (int k = 0; k < VB; k++) mn = fminf(mn, fmaf(nx, B.x[k], fmaf(ny, B.y[k], -c)));
-        sep = fmaxf(sep, mn);
-    }
-#pragma unroll
-    for (int e = 0; e < VB; e++) {
-        const float nx = B.ln[3 * e], ny = B.ln[3 * e + 1], c = B.ln[3 * e + 2];
-        float mn = BIG;
-#pragma unroll
-        for (int k = 0; k < VA; k++) mn = fminf(mn, fmaf(nx, A.x[k], fmaf(ny, A.y[k], -c)));
-        sep = fmaxf(sep, mn);
-    }
+    for (int e = 0; e < VB; e += 2)
+        sep = max3(sep, min_dist<VA>(A, B.ln[3 * e], B.ln[3 * e + 1], B.ln[3 * e + 2]),
+                   min_dist<VA>(A, B.ln[3 * e + 3], B.ln[3 * e + 4], B.ln[3 * e + 5]));
     return sep;
 }
 
@@ -351,7 +377,7 @@ __device__ __forceinline__ float sat_segment(const PolyRegs<VA> &A, const float4
         const float nx = A.ln[3 * e], ny = A.ln[3 * e + 1], c = A.ln[3 * e + 2];
         const float d0 = fmaf(nx, sa.x, fmaf(ny, sa.y, -c)), d1 = fmaf(nx, sa.z, fmaf(ny, sa.w, -c));
         sep = fmaxf(sep, fminf(d0, d1));
-        const float d = fmaf(sl.x, A.x[e], fmaf(sl.y, A.y[e], -sl.z));
+        const float d = fmaf(sl.x, A.x(e), fmaf(sl.y, A.y(e), -sl.z));
         mn = fminf(mn, d);
         mx = fmaxf(mx, d);
     }
@@ -362,7 +388,7 @@ constexpr int K_THREADS = 256;      // 8 warps share one staged tile
 constexpr int QCAP = 64;            // per-warp queue of (lane, record) pairs that passed axis 0
 
 template <int VA, int VB, bool COUNT, bool NOCULL>
-__global__ void __launch_bounds__(K_THREADS, NOCULL ? 2 : 4) k_check(const KParams p) {
+__global__ void __launch_bounds__(K_THREADS, 4) k_check(const KParams p) {
     constexpr int F = ob_fields(VB), FA = ob_fields(VA), NW = K_THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_raw);
@@ -470,7 +496,7 @@ __global__ void __launch_bounds__(K_THREADS, NOCULL ? 2 : 4) k_check(const KPara
                     ln[3 * e + 2] = (e < nv) ? fmaf(ln[3 * e], ax[e], ln[3 * e + 1] * ay[e]) : BIG;
                 __syncwarp();                       // previous group's readers are done with sA
 #pragma unroll
-                for (int h = 0; h < VA / 2; h++) sA[h * 32 + lane] = make_float4(ax[2 * h], ay[2 * h], ax[2 * h + 1], ay[2 * h + 1]);
+                for (int h = 0; h < VA / 2; h++) sA[h * 32 + lane] = make_float4(ax[2 * h], ax[2 * h + 1], ay[2 * h], ay[2 * h + 1]);
 #pragma unroll
                 for (int h = 0; h < (VA * 3 + 3) / 4; h++)
                     sA[(VA / 2 + h) * 32 + lane] = make_float4(ln[4 * h], ln[4 * h + 1], ln[4 * h + 2], ln[4 * h + 3]);
@@ -956,6 +982,20 @@ extern "C" int mpc_device_info(mpc_ctx *ctx, mpc_devinfo *out) {
     out->global_mem = (int64_t)ctx->prop.totalGlobalMem;
     out->l2_bytes = ctx->prop.l2CacheSize;
     out->abi_version = MPC_ABI_VERSION;
+    return MPC_OK;
+}
+
+extern "C" int mpc_alloc_pinned(mpc_ctx *ctx, uint64_t bytes, void **out) {
+    if (!ctx || !ctx->stream || !out) return MPC_E_ARG;
+    *out = nullptr;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMallocHost(out, (size_t)std::max<uint64_t>(bytes, 16)));
+    return MPC_OK;
+}
+
+extern "C" int mpc_free_pinned(mpc_ctx *ctx, void *ptr) {
+    if (!ctx || !ctx->stream) return MPC_E_ARG;
+    if (ptr) CU(cudaFreeHost(ptr));
     return MPC_OK;
 }
 

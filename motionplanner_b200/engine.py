@@ -62,6 +62,9 @@ class CollisionEngine:
 
     def close(self):
         if getattr(self, "_ctx", None):
+            for ptr in getattr(self, '_pinned', []):
+                self._L.mpc_free_pinned(self._ctx, ptr)
+            self._pinned = []
             self._L.mpc_destroy(self._ctx)
             self._ctx = C.c_void_p()
 
@@ -81,6 +84,18 @@ class CollisionEngine:
         return dict(name=info.name.decode(), sm_count=info.sm_count, cc=(info.cc_major, info.cc_minor),
                     clock_khz=info.clock_khz, global_mem=info.global_mem, l2_bytes=info.l2_bytes,
                     abi_version=info.abi_version)
+
+    def pinned_like(self, array):
+        """copy of `array` in page-locked host memory (mpc_alloc_pinned): host->device copies from it are real DMA"""
+        a = np.ascontiguousarray(array)
+        ptr = C.c_void_p()
+        self._check(self._L.mpc_alloc_pinned(self._ctx, max(a.nbytes, 16), C.byref(ptr)), "mpc_alloc_pinned")
+        buf = (C.c_char * max(a.nbytes, 16)).from_address(ptr.value)
+        out = np.frombuffer(buf, dtype=a.dtype, count=a.size).reshape(a.shape)
+        out[...] = a
+        self._pinned = getattr(self, '_pinned', [])
+        self._pinned.append(ptr)
+        return out
 
     # -- library -------------------------------------------------------------------------------------------------
     def upload_library(self, verts, nv, tidx, set_off=None, set_idx=None):
