@@ -269,3 +269,52 @@ def test_repeatability_under_load(eng):
     for _ in range(25):
         got, _ = eng.query(q, None, MODE_PLANNER)
         assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("nring", [24, 300, 1500])
+def test_parity_adversarial_vertex_alignments(eng, nring):
+    """inside/outside parity of the occupancy centre when many boundary vertices share (exactly, or within 1e-12 ..
+    1e-4 m) the centre's x or y: the float32 straddle tests then disagree with float64 for individual segments, and
+    only their consistency between neighbouring segments keeps the crossing parity right.
+    Star-shaped region with a star-shaped hole, both with `nring` vertices; every ray direction is exercised because
+    the per-warp direction choice depends on the block layout."""
+    rng = np.random.default_rng(nring)
+    P, J = 160, 2
+    verts = np.zeros((P, J, 4, 2))
+    cx = rng.uniform(-30, 30, (P, J))
+    cy = rng.uniform(-30, 30, (P, J))
+    for p in range(P):
+        for j in range(J):
+            verts[p, j] = W.rect_vertices(np.array(cx[p, j]), np.array(cy[p, j]), np.array(rng.uniform(-3, 3)), 1.2, 0.6)[::-1]
+    lib = dict(verts=verts, nv=np.full((P, J), 4, np.int32), tidx=np.tile(np.arange(J, dtype=np.int32), (P, 1)),
+               set_off=np.array([0, P], np.int32), set_idx=np.arange(P, dtype=np.int32))
+    pose = (3.25, -1.5)            # identity rotation: world centre = local centre + pose (up to one rounding)
+    wx, wy = (verts[..., 0].mean(-1) + pose[0]).ravel(), (verts[..., 1].mean(-1) + pose[1]).ravel()
+
+    def star(n, r0, r1, phase):
+        ang = np.sort(rng.uniform(0, 2 * np.pi, n)) + phase
+        r = rng.uniform(r0, r1, n)
+        ring = np.stack([r * np.cos(ang) + pose[0], r * np.sin(ang) + pose[1]], -1)
+        # align a third of the vertices with some centre coordinate, exactly or nearly
+        # (the nearest centre coordinate is used, so the ring keeps its shape)
+        for k in rng.choice(n, n // 3, replace=False):
+            d = rng.choice([0.0, 1e-12, -1e-12, 1e-9, -1e-9, 1e-7, -1e-7, 1e-5, -1e-5, 1e-4, -1e-4])
+            if rng.random() < 0.5:
+                ring[k, 1] = wy[np.argmin(np.abs(wy - ring[k, 1]))] + d
+            else:
+                ring[k, 0] = wx[np.argmin(np.abs(wx - ring[k, 0]))] + d
+        return ring
+
+    outer, hole = star(nring, 38.0, 60.0, 0.0), star(nring, 4.0, 9.0, 0.3)
+    seg = lambda r: np.concatenate([r, np.roll(r, -1, axis=0)], axis=1)
+    segs = np.concatenate([seg(outer), seg(hole)])
+    nsteps = 2
+    sc = dict(scene_step_off=np.array([0, nsteps], np.int32), step_obst_off=np.zeros(nsteps + 1, np.int32),
+              obst=np.zeros((0, 4, 2)), obst_nv=np.zeros(0, np.int32), step_seg_begin=np.zeros(nsteps, np.int32),
+              step_seg_end=np.full(nsteps, len(segs), np.int32), segs=segs)
+    q = make_queries(1)
+    q['x'], q['y'], q['cand_set'], q['cand_cnt'] = pose[0], pose[1], 0, P
+    for origin in (np.array([pose]), np.array([[pose[0] + 700.0, pose[1] - 900.0]])):    # tight and loose band
+        got, want, st, ost = both(eng, lib, sc, origin, q, None, MODE_PLANNER)
+        assert np.array_equal(got, want), "parity disagreements: %d" % (got != want).sum()
+    assert 0 < want.mean() < 1
