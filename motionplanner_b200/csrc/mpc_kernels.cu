@@ -32,6 +32,7 @@
 #include <string>
 #include <vector>
 
+
 #include "../../include/mpc.h"
 #include "mpc_exact.cuh"
 
@@ -81,7 +82,8 @@ struct KParams {
     int4 *wl;
     int wl_cap;
     Counters *cnt;
-    float maxabs_query, lib_rmax;
+    const float *maxabs_query;   // batch header in the query pack (device), so that a captured graph stays valid
+    float lib_rmax;
     unsigned mode;
     int gpc, cap_o, cap_s;
 };
@@ -424,7 +426,7 @@ __global__ void __launch_bounds__(K_THREADS, 4) k_check(const KParams p) {
     const int ng = min(p.gpc, (cand_cnt + 31) / 32 - gbeg);
     const float lx = Q->lx, ly = Q->ly, lc = Q->lc, ls = Q->ls;
     // float32 error band: every float32 signed distance below is within tau of its float64 value
-    const float tau = fmaxf(fmaxf(*p.maxabs_scene, p.maxabs_query) * (1.0f / 131072.0f), 1e-7f);
+    const float tau = fmaxf(fmaxf(*p.maxabs_scene, *p.maxabs_query) * (1.0f / 131072.0f), 1e-7f);
     const bool noexit = p.mode & MPC_MODE_NO_EARLY_EXIT;
 
     if (tid == 0) mbar_init(bar, 1);
@@ -863,7 +865,9 @@ struct mpc_ctx {
     float maxabs_scene = 0.f;
     // queries
     DevBuf qpack_d, cand_d, res_d, wl, flush;
-    size_t qpack_cta_off = 0;
+    size_t qpack_cta_off = 0, qpack_hdr_off = 0, up_bytes = 0, up_cand_bytes = 0, up_cand_src = 0;
+    unsigned long long generation = 0;          // bumped whenever a pointer a captured graph holds may have changed
+    std::map<std::vector<long long>, cudaGraphExec_t> graphs;
     void *h_res = nullptr;
     size_t h_res_cap = 0;
     std::map<int, size_t> smem_attr;
@@ -895,8 +899,12 @@ static int fail(mpc_ctx *ctx, int code, const char *fmt, ...) {
             return fail(ctx, MPC_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-static cudaError_t ensure(DevBuf &b, size_t bytes) {
+static void invalidate_graphs(mpc_ctx *ctx);
+
+// grow-only device buffer; a reallocation moves pointers that captured graphs hold, so it drops them
+static cudaError_t ensure(mpc_ctx *ctx, DevBuf &b, size_t bytes) {
     if (bytes <= b.cap && b.p) return cudaSuccess;
+    invalidate_graphs(ctx);
     if (b.p) cudaFree(b.p);
     b.p = nullptr;
     b.cap = 0;
@@ -906,8 +914,16 @@ static cudaError_t ensure(DevBuf &b, size_t bytes) {
     return e;
 }
 
+static void invalidate_graphs(mpc_ctx *ctx) {
+    for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+    ctx->graphs.clear();
+    ctx->generation++;
+}
+
 static cudaError_t ensure_pinned(mpc_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->h_pin_cap) return cudaSuccess;
+    invalidate_graphs(ctx);
+    for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     ctx->h_pin = nullptr;
     ctx->h_pin_cap = 0;
@@ -938,11 +954,11 @@ extern "C" int mpc_create(int device, mpc_ctx **out) {
     if (ctx->prop.major < 9) return fail(ctx, MPC_E_CUDA, "device sm_%d%d lacks TMA bulk copies; built for sm_100a", ctx->prop.major, ctx->prop.minor);
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (auto &ev : ctx->ev) CU(cudaEventCreate(&ev));
-    CU(ensure(ctx->res_d, sizeof(Counters) + 4096));
-    CU(ensure(ctx->maxabs, sizeof(float)));
+    CU(ensure(ctx, ctx->res_d, sizeof(Counters) + 4096));
+    CU(ensure(ctx, ctx->maxabs, sizeof(float)));
     CU(cudaMemsetAsync(ctx->maxabs.p, 0, sizeof(float), ctx->stream));
     ctx->wl_cap = 1 << 18;
-    CU(ensure(ctx->wl, sizeof(int4) * (size_t)ctx->wl_cap));
+    CU(ensure(ctx, ctx->wl, sizeof(int4) * (size_t)ctx->wl_cap));
     return MPC_OK;
 }
 
@@ -960,6 +976,7 @@ extern "C" void mpc_destroy(mpc_ctx *ctx) {
                       &ctx->flush};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
+    for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     for (auto &ev : ctx->ev)
@@ -1078,12 +1095,12 @@ extern "C" int mpc_upload_library(mpc_ctx *ctx, const double *verts, const int32
     }
     // note: a zero-length edge keeps normal (0,0); k_check turns its line into "never separating" only for e >= nv,
     // so give such edges the same treatment by dropping them here
-    CU(ensure(ctx->lib_v, hv.size() * sizeof(float4)));
-    CU(ensure(ctx->lib_n, hn.size() * sizeof(float4)));
-    CU(ensure(ctx->lib_c, hc.size() * sizeof(float4)));
-    CU(ensure(ctx->lib_v64, h64.size() * sizeof(double)));
-    CU(ensure(ctx->lib_nv, hnv.size() * sizeof(int)));
-    CU(ensure(ctx->slot_t, slot_t.size() * sizeof(int)));
+    CU(ensure(ctx, ctx->lib_v, hv.size() * sizeof(float4)));
+    CU(ensure(ctx, ctx->lib_n, hn.size() * sizeof(float4)));
+    CU(ensure(ctx, ctx->lib_c, hc.size() * sizeof(float4)));
+    CU(ensure(ctx, ctx->lib_v64, h64.size() * sizeof(double)));
+    CU(ensure(ctx, ctx->lib_nv, hnv.size() * sizeof(int)));
+    CU(ensure(ctx, ctx->slot_t, slot_t.size() * sizeof(int)));
     CU(cudaMemcpyAsync(ctx->lib_v.p, hv.data(), hv.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->lib_n.p, hn.data(), hn.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->lib_c.p, hc.data(), hc.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
@@ -1103,11 +1120,12 @@ extern "C" int mpc_upload_library(mpc_ctx *ctx, const double *verts, const int32
         ctx->set_off.assign(set_off, set_off + nsets + 1);
         ctx->nsets = nsets;
         ctx->set_total = total;
-        CU(ensure(ctx->sets, std::max<size_t>(total, 1) * sizeof(int)));
+        CU(ensure(ctx, ctx->sets, std::max<size_t>(total, 1) * sizeof(int)));
         if (total) CU(cudaMemcpyAsync(ctx->sets.p, set_idx, (size_t)total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->P = P; ctx->J = J; ctx->lib_vmax = VA; ctx->VA = VA; ctx->lib_radius = radius; ctx->lib_rmax = rmax;
+    invalidate_graphs(ctx);
     ctx->have_lib = true;
     ctx->prepared = false;
     ctx->arena_valid = false;
@@ -1206,23 +1224,23 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     }
     const int noslots = slot_off[nsteps];
     const int ob_stride = std::max(noslots, 32), sg_stride = std::max(nslots, 32);
-    CU(ensure(ctx->scene_step_off_d, (size_t)(nscenes + 1) * sizeof(int)));
-    CU(ensure(ctx->origins_d, (size_t)nscenes * 2 * sizeof(double)));
-    CU(ensure(ctx->step_obst_off, (size_t)(nsteps + 1) * sizeof(int)));
-    CU(ensure(ctx->step_seg_begin, (size_t)std::max(nsteps, 1) * sizeof(int)));
-    CU(ensure(ctx->step_seg_end, (size_t)std::max(nsteps, 1) * sizeof(int)));
-    CU(ensure(ctx->ob_src, (size_t)std::max(nobst, 1) * VB * 2 * sizeof(double)));
-    CU(ensure(ctx->ob_src_nv, (size_t)std::max(nobst, 1) * sizeof(int)));
-    CU(ensure(ctx->ob_src_off, (size_t)(nsteps + 1) * sizeof(int)));
-    CU(ensure(ctx->step_obst_cnt, (size_t)std::max(nsteps, 1) * sizeof(int)));
-    CU(ensure(ctx->ob_in, (size_t)ob_stride * VB * 2 * sizeof(double)));
-    CU(ensure(ctx->ob_nv, (size_t)ob_stride * sizeof(int)));
-    CU(ensure(ctx->ob_f, (size_t)ob_stride * F * sizeof(float4)));
-    CU(ensure(ctx->ob_c, (size_t)ob_stride * 3 * sizeof(float)));
-    CU(ensure(ctx->sg_64, (size_t)sg_stride * 4 * sizeof(double)));
-    CU(ensure(ctx->sg_f, (size_t)sg_stride * 2 * sizeof(float4)));
-    CU(ensure(ctx->sg_box, (size_t)(sg_stride / 32 + 1) * sizeof(float4)));
-    CU(ensure(ctx->seg_scene, (size_t)sg_stride * sizeof(int)));
+    CU(ensure(ctx, ctx->scene_step_off_d, (size_t)(nscenes + 1) * sizeof(int)));
+    CU(ensure(ctx, ctx->origins_d, (size_t)nscenes * 2 * sizeof(double)));
+    CU(ensure(ctx, ctx->step_obst_off, (size_t)(nsteps + 1) * sizeof(int)));
+    CU(ensure(ctx, ctx->step_seg_begin, (size_t)std::max(nsteps, 1) * sizeof(int)));
+    CU(ensure(ctx, ctx->step_seg_end, (size_t)std::max(nsteps, 1) * sizeof(int)));
+    CU(ensure(ctx, ctx->ob_src, (size_t)std::max(nobst, 1) * VB * 2 * sizeof(double)));
+    CU(ensure(ctx, ctx->ob_src_nv, (size_t)std::max(nobst, 1) * sizeof(int)));
+    CU(ensure(ctx, ctx->ob_src_off, (size_t)(nsteps + 1) * sizeof(int)));
+    CU(ensure(ctx, ctx->step_obst_cnt, (size_t)std::max(nsteps, 1) * sizeof(int)));
+    CU(ensure(ctx, ctx->ob_in, (size_t)ob_stride * VB * 2 * sizeof(double)));
+    CU(ensure(ctx, ctx->ob_nv, (size_t)ob_stride * sizeof(int)));
+    CU(ensure(ctx, ctx->ob_f, (size_t)ob_stride * F * sizeof(float4)));
+    CU(ensure(ctx, ctx->ob_c, (size_t)ob_stride * 3 * sizeof(float)));
+    CU(ensure(ctx, ctx->sg_64, (size_t)sg_stride * 4 * sizeof(double)));
+    CU(ensure(ctx, ctx->sg_f, (size_t)sg_stride * 2 * sizeof(float4)));
+    CU(ensure(ctx, ctx->sg_box, (size_t)(sg_stride / 32 + 1) * sizeof(float4)));
+    CU(ensure(ctx, ctx->seg_scene, (size_t)sg_stride * sizeof(int)));
     cudaStream_t st = ctx->stream;
     CU(cudaMemcpyAsync(ctx->scene_step_off_d.p, scene_step_off, (size_t)(nscenes + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ctx->origins_d.p, origins, (size_t)nscenes * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -1271,6 +1289,7 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     ctx->ob_vmax = VB; ctx->VB = VB; ctx->max_obst_step = max_o; ctx->max_seg_step = max_s;
     ctx->scene_step_off.assign(scene_step_off, scene_step_off + nscenes + 1);
     ctx->origins.assign(origins, origins + 2 * (size_t)nscenes);
+    invalidate_graphs(ctx);
     ctx->have_scenes = true;
     ctx->prepared = false;
     return MPC_OK;
@@ -1300,7 +1319,7 @@ static KParams make_params(mpc_ctx *ctx) {
     p.B = ctx->B;
     p.cnt = (Counters *)ctx->res_d.p; p.mask = (unsigned *)((char *)ctx->res_d.p + sizeof(Counters));
     p.wl = (int4 *)ctx->wl.p; p.wl_cap = ctx->wl_cap;
-    p.maxabs_query = ctx->maxabs_query; p.lib_rmax = ctx->lib_rmax; p.mode = ctx->mode;
+    p.maxabs_query = (const float *)(qp + ctx->qpack_hdr_off); p.lib_rmax = ctx->lib_rmax; p.mode = ctx->mode;
     p.gpc = ctx->gpc; p.cap_o = ctx->cap_o; p.cap_s = ctx->cap_s;
     return p;
 }
@@ -1344,8 +1363,11 @@ static int launch_all(mpc_ctx *ctx, cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t 
     return MPC_OK;
 }
 
-extern "C" int mpc_prepare_query(mpc_ctx *ctx, int B, const mpc_query_desc *queries, const int32_t *cand_idx, int ncand,
-                                 unsigned mode) {
+static int issue_uploads(mpc_ctx *ctx);
+static cudaError_t ensure_result_host(mpc_ctx *ctx, size_t bytes);
+
+static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, const int32_t *cand_idx, int ncand,
+                        unsigned mode, bool upload) {
     if (!ctx || !ctx->stream) return MPC_E_STATE;
     if (!ctx->have_lib || !ctx->have_scenes) return fail(ctx, MPC_E_STATE, "upload the library and the scenes before querying");
     if (B < 0 || (B > 0 && !queries)) return fail(ctx, MPC_E_ARG, "bad query arguments");
@@ -1382,11 +1404,13 @@ extern "C" int mpc_prepare_query(mpc_ctx *ctx, int B, const mpc_query_desc *quer
     ctx->smem = 16 + 3 * GPC_MAX * 4 + (size_t)nwarps * QCAP * 4 + (size_t)nwarps * FA * 32 * 16 +
                 (size_t)ctx->cap_o * (F * 16 + 12) + (size_t)ctx->cap_s * 32;
     // pack: QDev[B], cta_off[B+1] (one copy), explicit candidates (second copy, only when present)
-    size_t bytes_q = sizeof(QDev) * (size_t)std::max(B, 1), bytes_c = sizeof(int) * (size_t)(B + 1), bytes_i = sizeof(int) * (size_t)ncand;
-    CU(ensure_pinned(ctx, bytes_q + bytes_c + bytes_i + 64));
+    size_t bytes_q = sizeof(QDev) * (size_t)std::max(B, 1), bytes_c = (sizeof(int) * (size_t)(B + 1) + 15) / 16 * 16;
+    const size_t bytes_h = 16, bytes_i = sizeof(int) * (size_t)ncand;
+    CU(ensure_pinned(ctx, bytes_q + bytes_c + bytes_h + bytes_i + 64));
     QDev *hq = (QDev *)ctx->h_pin;
     int *hcta = (int *)((char *)ctx->h_pin + bytes_q);
-    int *hidx = (int *)((char *)ctx->h_pin + bytes_q + bytes_c);
+    float *hhdr = (float *)((char *)ctx->h_pin + bytes_q + bytes_c);
+    int *hidx = (int *)((char *)ctx->h_pin + bytes_q + bytes_c + bytes_h);
     long long ctas = 0, words = 0;
     double maxq = 0.0;
     for (int q = 0; q < B; q++) {
@@ -1412,22 +1436,42 @@ extern "C" int mpc_prepare_query(mpc_ctx *ctx, int B, const mpc_query_desc *quer
     hcta[B] = (int)ctas;
     if (ctas > 0x7fffffffLL || words > 0x7fffffffLL) return fail(ctx, MPC_E_LIMIT, "batch too large");
     if (ncand) memcpy(hidx, cand_idx, bytes_i);
-    CU(ensure(ctx->qpack_d, bytes_q + bytes_c));
+    ctx->maxabs_query = std::nextafter((float)maxq, INFINITY);
+    hhdr[0] = ctx->maxabs_query;
+    hhdr[1] = hhdr[2] = hhdr[3] = 0.f;
+    CU(ensure(ctx, ctx->qpack_d, bytes_q + bytes_c + bytes_h));
     ctx->qpack_cta_off = bytes_q;
+    ctx->qpack_hdr_off = bytes_q + bytes_c;
+    ctx->up_bytes = bytes_q + bytes_c + bytes_h;
+    ctx->up_cand_bytes = bytes_i;
+    ctx->up_cand_src = bytes_q + bytes_c + bytes_h;
     // candidate arena = staged sets followed by this call's explicit lists
     size_t arena = sizeof(int) * (size_t)std::max(ctx->set_total + ncand, 1);
     void *arena_before = ctx->cand_d.p;
-    CU(ensure(ctx->cand_d, arena));
+    CU(ensure(ctx, ctx->cand_d, arena));
     if ((ctx->cand_d.p != arena_before || !ctx->arena_valid) && ctx->set_total)
         CU(cudaMemcpyAsync(ctx->cand_d.p, ctx->sets.p, sizeof(int) * (size_t)ctx->set_total, cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->arena_valid = true;
-    CU(ensure(ctx->res_d, sizeof(Counters) + sizeof(unsigned) * (size_t)std::max<long long>(words, 1)));
-    CU(cudaMemcpyAsync(ctx->qpack_d.p, hq, bytes_q + bytes_c, cudaMemcpyHostToDevice, ctx->stream));
-    if (ncand) CU(cudaMemcpyAsync((int *)ctx->cand_d.p + ctx->set_total, hidx, bytes_i, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ensure(ctx, ctx->res_d, sizeof(Counters) + sizeof(unsigned) * (size_t)std::max<long long>(words, 1)));
+    CU(ensure_result_host(ctx, sizeof(Counters) + sizeof(unsigned) * (size_t)std::max<long long>(words, 1)));
     ctx->B = B; ctx->ctas = (int)ctas; ctx->mask_words = (int)words; ctx->mode = mode;
-    ctx->maxabs_query = std::nextafter((float)maxq, INFINITY);
     ctx->prepared = true;
+    if (upload) return issue_uploads(ctx);
     return MPC_OK;
+}
+
+// host -> device copies of the packed batch (pinned staging buffer -> query pack, explicit candidate lists)
+static int issue_uploads(mpc_ctx *ctx) {
+    CU(cudaMemcpyAsync(ctx->qpack_d.p, ctx->h_pin, ctx->up_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->up_cand_bytes)
+        CU(cudaMemcpyAsync((int *)ctx->cand_d.p + ctx->set_total, (const char *)ctx->h_pin + ctx->up_cand_src, ctx->up_cand_bytes,
+                           cudaMemcpyHostToDevice, ctx->stream));
+    return MPC_OK;
+}
+
+extern "C" int mpc_prepare_query(mpc_ctx *ctx, int B, const mpc_query_desc *queries, const int32_t *cand_idx, int ncand,
+                                 unsigned mode) {
+    return prepare_host(ctx, B, queries, cand_idx, ncand, mode, true);
 }
 
 static void fill_stats(mpc_ctx *ctx, mpc_stats *st, float ms, int kernels, int overflow) {
@@ -1449,6 +1493,7 @@ static void fill_stats(mpc_ctx *ctx, mpc_stats *st, float ms, int kernels, int o
 
 static cudaError_t ensure_result_host(mpc_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->h_res_cap) return cudaSuccess;
+    invalidate_graphs(ctx);
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     ctx->h_res = nullptr;
     ctx->h_res_cap = 0;
@@ -1477,20 +1522,69 @@ static int run_once(mpc_ctx *ctx, float *ms, int *kernels, int *overflow, bool t
         if (c->wl_count <= (unsigned)ctx->wl_cap) return MPC_OK;
         *overflow = 1;
         ctx->wl_cap = (int)std::min<unsigned long long>((unsigned long long)c->wl_count * 5 / 4 + 1024, 0x7fffffffULL / sizeof(int4));
-        CU(ensure(ctx->wl, sizeof(int4) * (size_t)ctx->wl_cap));
+        CU(ensure(ctx, ctx->wl, sizeof(int4) * (size_t)ctx->wl_cap));
     }
     return fail(ctx, MPC_E_LIMIT, "refinement list still overflows at %d entries", ctx->wl_cap);
 }
 
+// the whole query as one CUDA graph: H2D of the batch, clear, k_check, k_refine, D2H of the result block.  A planner
+// issues hundreds of small queries of a handful of shapes; replaying an instantiated graph replaces six driver calls
+// by one.  Graphs are keyed by everything that is baked into their nodes and dropped whenever a buffer moves.
+static int run_graph(mpc_ctx *ctx, float *ms, bool timed) {
+    const size_t bytes = sizeof(Counters) + (size_t)ctx->mask_words * sizeof(unsigned);
+    std::vector<long long> key = {(long long)ctx->B, (long long)ctx->ctas, (long long)ctx->mask_words, (long long)ctx->mode,
+                                  (long long)ctx->gpc, (long long)ctx->cap_o, (long long)ctx->cap_s, (long long)ctx->smem,
+                                  (long long)ctx->up_bytes, (long long)ctx->up_cand_bytes, (long long)ctx->wl_cap,
+                                  (long long)ctx->VA, (long long)ctx->VB};
+    auto it = ctx->graphs.find(key);
+    if (it == ctx->graphs.end()) {
+        if (ctx->graphs.size() > 256) invalidate_graphs(ctx);
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = issue_uploads(ctx);
+        if (!rc) rc = launch_all(ctx, nullptr, nullptr, nullptr);
+        cudaError_t e1 = cudaSuccess;
+        if (!rc) e1 = cudaMemcpyAsync(ctx->h_res, ctx->res_d.p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e2 = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            return fail(ctx, MPC_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        }
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t e3 = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e3 != cudaSuccess) return fail(ctx, MPC_E_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e3));
+        it = ctx->graphs.emplace(key, exec).first;
+    }
+    if (timed) CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CU(cudaGraphLaunch(it->second, ctx->stream));
+    if (timed) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (timed) CU(cudaEventElapsedTime(ms, ctx->ev[0], ctx->ev[1]));
+    return MPC_OK;
+}
+
 extern "C" int mpc_query(mpc_ctx *ctx, int B, const mpc_query_desc *queries, const int32_t *cand_idx, int ncand,
                          unsigned mode, uint32_t *out_mask, int mask_words, mpc_stats *stats) {
-    int rc = mpc_prepare_query(ctx, B, queries, cand_idx, ncand, mode);
+    int rc = prepare_host(ctx, B, queries, cand_idx, ncand, mode, false);
     if (rc) return rc;
     if (mask_words != ctx->mask_words) return fail(ctx, MPC_E_ARG, "mask_words=%d but the batch needs %d", mask_words, ctx->mask_words);
     if (mask_words > 0 && !out_mask) return fail(ctx, MPC_E_ARG, "out_mask missing");
     float ms = 0.f;
-    int kernels = 0, overflow = 0;
-    rc = run_once(ctx, &ms, &kernels, &overflow, stats != nullptr);
+    int kernels = 2, overflow = 0;
+    if (ctx->smem > 48 * 1024) {          // large tiles need the opt-in attribute, which cannot be set during capture
+        rc = issue_uploads(ctx);
+        if (!rc) rc = run_once(ctx, &ms, &kernels, &overflow, stats != nullptr);
+    } else {
+        rc = run_graph(ctx, &ms, stats != nullptr);
+        if (!rc && ((const Counters *)ctx->h_res)->wl_count > (unsigned)ctx->wl_cap) {
+            // refinement list overflowed: the plain path grows it and re-runs (and drops the graphs)
+            rc = issue_uploads(ctx);
+            if (!rc) rc = run_once(ctx, &ms, &kernels, &overflow, stats != nullptr);
+            overflow = 1;
+        }
+    }
     if (rc) return rc;
     if (mask_words) memcpy(out_mask, (const char *)ctx->h_res + sizeof(Counters), sizeof(unsigned) * (size_t)mask_words);
     fill_stats(ctx, stats, ms, kernels, overflow);
@@ -1506,7 +1600,7 @@ extern "C" int mpc_run_prepared(mpc_ctx *ctx, int iters, int flush_l2, float *ms
     int rc = run_once(ctx, &ms, &kernels, &overflow, true);     // sizes the refinement list
     if (rc) return rc;
     const size_t flush_bytes = 256u << 20;
-    if (flush_l2) CU(ensure(ctx->flush, flush_bytes));
+    if (flush_l2) CU(ensure(ctx, ctx->flush, flush_bytes));
     for (int it = 0; it < iters; it++) {
         if (flush_l2) {
             k_fill_u32<<<ctx->prop.multiProcessorCount * 8, 256, 0, ctx->stream>>>((unsigned *)ctx->flush.p, flush_bytes / 4, (unsigned)it);
