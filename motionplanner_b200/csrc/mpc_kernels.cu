@@ -27,6 +27,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -958,6 +959,7 @@ extern "C" int mpc_create(int device, mpc_ctx **out) {
     CU(ensure(ctx, ctx->maxabs, sizeof(float)));
     CU(cudaMemsetAsync(ctx->maxabs.p, 0, sizeof(float), ctx->stream));
     ctx->wl_cap = 1 << 18;
+    if (const char *e = getenv("MPC_WL_CAP")) ctx->wl_cap = std::max(1, atoi(e));      // test hook: force the overflow path
     CU(ensure(ctx, ctx->wl, sizeof(int4) * (size_t)ctx->wl_cap));
     return MPC_OK;
 }

@@ -318,3 +318,42 @@ def test_parity_adversarial_vertex_alignments(eng, nring):
         got, want, st, ost = both(eng, lib, sc, origin, q, None, MODE_PLANNER)
         assert np.array_equal(got, want), "parity disagreements: %d" % (got != want).sum()
     assert 0 < want.mean() < 1
+
+
+def test_dense_general_polygons_multi_phase_and_queue_pressure(eng):
+    """8-gons on both sides, 300 obstacles per step (two tiles), candidates clustered on the obstacles so that most
+    axis-0 tests pass: the per-warp queues fill and drain many times per tile"""
+    rng = np.random.default_rng(8)
+    lib, sc, org, q = W.adversarial_problem(500, P=128, J=3, nsteps=4, max_obst=5, lib_verts=8, obst_verts=8)
+    nsteps, O = 4, 300
+    obst = np.zeros((nsteps * O, 8, 2))
+    nv = np.zeros(nsteps * O, np.int32)
+    for k in range(nsteps * O):
+        n = int(rng.integers(3, 9))
+        poly = W.random_convex(rng, n, rng.uniform(1.0, 4.0)) + [rng.uniform(-10, 60), rng.uniform(-30, 30)]
+        obst[k, :n] = poly if rng.random() < 0.5 else poly[::-1]
+        nv[k] = n
+    sc["obst"], sc["obst_nv"] = obst, nv
+    sc["step_obst_off"] = (np.arange(nsteps + 1) * O).astype(np.int32)
+    for mode in (MODE_PLANNER, MODE_VALIDATOR | MODE_NO_EARLY_EXIT, MODE_NO_CULL):
+        got, want, st, ost = both(eng, lib, sc, org, q, None, mode)
+        assert np.array_equal(got, want), mode
+        assert st["pairs_nominal"] == ost["pairs_nominal"]
+    got, st = eng.query(q, None, MODE_COUNT_WORK | MODE_NO_EARLY_EXIT)
+    assert st["axis_tests"] > 0.01 * st["pairs_nominal"]          # the queue path really carried a lot of pairs
+
+
+def test_refinement_list_overflow_is_recovered(monkeypatch):
+    """more pairs inside the float32 band than the refinement list holds: the call grows the list and re-runs"""
+    monkeypatch.setenv("MPC_WL_CAP", "8")
+    e2 = CollisionEngine(0)
+    monkeypatch.delenv("MPC_WL_CAP")
+    lib, sc, org, q = W.adversarial_problem(7, P=200, max_obst=70)
+    stage(e2, lib, sc, org)
+    got, st = e2.query(q, None, MODE_PLANNER)
+    want, _ = orc.Problem(lib, sc).check(q, None, orc.MODE_NO_EARLY_EXIT)
+    assert np.array_equal(got, want)
+    assert st["worklist_overflow"] == 1 and st["refined_fp64"] > 8
+    got, st = e2.query(q, None, MODE_PLANNER)                       # the grown list is kept
+    assert np.array_equal(got, want) and st["worklist_overflow"] == 0
+    e2.close()
