@@ -1,7 +1,7 @@
 // mpc_exact.cuh -- float64 tie-breaking pass: exact orientation signs on the device.
 //
 // The float32 separating-axis kernel (mpc_kernels.cu) decides a pair only when the separation is outside a
-// conservative error band; the pairs inside the band come here.  Everything below is evaluated on the SAME float64
+// conservative error band; the pairs inside the band are re-decided by k_refine with the predicate below.  Everything below is evaluated on the SAME float64
 // vertices the reference hands to GEOS (shapely affine_transform arithmetic, src/lowLevelPlannerManeuverAutomaton.py:121),
 // and every orientation sign is exact: a forward-error filter first, then non-overlapping expansion arithmetic
 // (two-sum / FMA two-product) when the filter cannot decide.  So the final decision equals the decision exact rational
@@ -13,11 +13,6 @@
 #include <cstdint>
 
 namespace mpc {
-
-struct Poly64 {
-    int n;
-    double x[16], y[16];
-};
 
 __device__ __forceinline__ void two_sum(double a, double b, double &s, double &e) {
     s = __dadd_rn(a, b);
@@ -70,70 +65,6 @@ __device__ __forceinline__ int orient2d(double ax, double ay, double bx, double 
     if (-det > errbound) return -1;
     ties++;
     return orient_exact(ax, ay, bx, by, cx, cy);
-}
-
-// an edge of the CCW convex polygon A has every vertex of B on its outer side (strict: strictly outside)
-__device__ inline bool separated_by_edge_of(const Poly64 &A, const Poly64 &B, bool strict, unsigned &ties) {
-    for (int i = 0; i < A.n; i++) {
-        int k = (i + 1 == A.n) ? 0 : i + 1;
-        if (A.x[i] == A.x[k] && A.y[i] == A.y[k]) continue;
-        bool all_out = true;
-        for (int q = 0; q < B.n; q++) {
-            int o = orient2d(A.x[i], A.y[i], A.x[k], A.y[k], B.x[q], B.y[q], ties);
-            if (strict ? (o >= 0) : (o > 0)) { all_out = false; break; }
-        }
-        if (all_out) return true;
-    }
-    return false;
-}
-
-// strict: closed polygons share a point (shapely intersects); else: open interiors share a point
-__device__ inline bool convex_collide(const Poly64 &A, const Poly64 &B, bool strict, unsigned &ties) {
-    if (separated_by_edge_of(A, B, strict, ties)) return false;
-    if (separated_by_edge_of(B, A, strict, ties)) return false;
-    return true;
-}
-
-// closed segment has a point in the open interior of the CCW convex polygon P
-__device__ inline bool segment_meets_interior(const Poly64 &P, double s0x, double s0y, double s1x, double s1y,
-                                              unsigned &ties) {
-    for (int i = 0; i < P.n; i++) {
-        int k = (i + 1 == P.n) ? 0 : i + 1;
-        if (P.x[i] == P.x[k] && P.y[i] == P.y[k]) continue;
-        if (orient2d(P.x[i], P.y[i], P.x[k], P.y[k], s0x, s0y, ties) <= 0 &&
-            orient2d(P.x[i], P.y[i], P.x[k], P.y[k], s1x, s1y, ties) <= 0)
-            return false;
-    }
-    if (s0x == s1x && s0y == s1y) return true;
-    bool pos = false, neg = false;
-    for (int q = 0; q < P.n; q++) {
-        int o = orient2d(s0x, s0y, s1x, s1y, P.x[q], P.y[q], ties);
-        pos |= o > 0;
-        neg |= o < 0;
-    }
-    return pos && neg;
-}
-
-// approximate separation in metres (> 0 apart); only feeds the near-tangent statistic
-__device__ inline double approx_sep(const Poly64 &A, const Poly64 &B) {
-    double best = -1e300;
-    for (int pass = 0; pass < 2; pass++) {
-        const Poly64 &P = pass ? B : A;
-        const Poly64 &Q = pass ? A : B;
-        for (int i = 0; i < P.n; i++) {
-            int k = (i + 1 == P.n) ? 0 : i + 1;
-            double ex = P.x[k] - P.x[i], ey = P.y[k] - P.y[i];
-            double len = sqrt(ex * ex + ey * ey);
-            if (len == 0.0) continue;
-            double mn = 1e300;
-            for (int q = 0; q < Q.n; q++) {
-                double d = (ey * (Q.x[q] - P.x[i]) - ex * (Q.y[q] - P.y[i])) / len;
-                mn = fmin(mn, d);
-            }
-            best = fmax(best, mn);
-        }
-    }
-    return best;
 }
 
 }  // namespace mpc

@@ -735,80 +735,124 @@ __global__ void __launch_bounds__(K_THREADS, 4) k_check(const KParams p) {
 // ---------------------------------------------------------------------------------------------------------------------
 // float64 / exact refinement of the pairs inside the float32 band
 // ---------------------------------------------------------------------------------------------------------------------
+// One WARP per work-list item: the orientation tests of an item (up to nA*nB of them per direction) are independent,
+// so the lanes split them and votes put the answer together.  A single thread needs ~20 k cycles per polygon pair
+// (dependent float64 chains, local-memory polygon arrays); a warp needs ~1-2 k, which is what a planner that waits on
+// every query cares about.
 __global__ void __launch_bounds__(128) k_refine(const KParams p) {
+    __shared__ double s_pts[4][2 * (MPC_MAX_LIB_VERTS + MPC_MAX_OBST_VERTS)];
     const unsigned n = min(p.cnt->wl_count, (unsigned)p.wl_cap);
+    const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+    double *Ax = s_pts[wib], *Ay = Ax + MPC_MAX_LIB_VERTS, *Bx = Ay + MPC_MAX_LIB_VERTS, *By = Bx + MPC_MAX_OBST_VERTS;
     unsigned refined = 0, ties = 0, near_t = 0, par_ref = 0;
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned nthreads = gridDim.x * blockDim.x;
-    for (unsigned base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += nthreads) {   // warp-uniform
-        const unsigned idx = base + lane;
-        const bool have = idx < n;
-        int q = 0, ci = 0, kind = -1;
-        const QDev *Q = p.q;
-        Poly64 A;
-        A.n = 0;
-        bool collide = false;
-        double cx = 0.0, cy = 0.0;
-        int g0 = 0, g1 = 0;
-        if (have) {
-            const int4 e = p.wl[idx];
-            q = e.x; ci = e.y; kind = e.z >> 16;
-            const int j = e.z & 0xffff, obj = e.w;
-            Q = p.q + q;
-            const int pj = p.cand[Q->cand_base + ci] * p.J + j;
-            A.n = p.lib_nv[pj];
-            const double *lv = p.lib_v64 + (size_t)pj * p.lib_vmax * 2;
+    const bool strict = p.mode & MPC_MODE_VALIDATOR;
+    for (unsigned item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n; item += warps) {
+        const int4 e = p.wl[item];
+        const int q = e.x, ci = e.y, j = e.z & 0xffff, kind = e.z >> 16, obj = e.w;
+        const QDev *Q = p.q + q;
+        const int pj = p.cand[Q->cand_base + ci] * p.J + j;
+        const int nA = p.lib_nv[pj];
+        __syncwarp();
+        if ((int)lane < nA) {
+            const double *lv = p.lib_v64 + ((size_t)pj * p.lib_vmax + lane) * 2;
             // shapely affine_transform(o['space'], [cos, -sin, sin, cos, x, y]): xp = a*x + b*y + xoff, left to right
-            const double a = Q->c, b = -Q->s, d = Q->s, ee = Q->c;
-            for (int k = 0; k < A.n; k++) {
-                A.x[k] = __dadd_rn(__dadd_rn(__dmul_rn(a, lv[2 * k]), __dmul_rn(b, lv[2 * k + 1])), Q->x);
-                A.y[k] = __dadd_rn(__dadd_rn(__dmul_rn(d, lv[2 * k]), __dmul_rn(ee, lv[2 * k + 1])), Q->y);
-            }
-            if (kind == KIND_OBST) {
-                Poly64 Bp;
-                Bp.n = p.ob_nv[obj];
-                const double *bv = p.ob_v64 + (size_t)obj * p.ob_vmax * 2;
-                for (int k = 0; k < Bp.n; k++) { Bp.x[k] = bv[2 * k]; Bp.y[k] = bv[2 * k + 1]; }
-                collide = convex_collide(A, Bp, p.mode & MPC_MODE_VALIDATOR, ties);
-                if (fabs(approx_sep(A, Bp)) < 1e-9) near_t++;
-                refined++;
-            } else if (kind == KIND_SEG) {
-                const double *sg = p.sg_64 + 4 * (size_t)obj;
-                collide = segment_meets_interior(A, sg[0], sg[1], sg[2], sg[3], ties);
-                refined++;
-            } else {
-                for (int k = 0; k < A.n; k++) { cx += A.x[k]; cy += A.y[k]; }
-                cx /= A.n; cy /= A.n;
-                const int step = Q->step0 + Q->t0 + p.slot_t[j];
-                g0 = p.step_seg_begin[step];
-                g1 = p.step_seg_end[step];
-                par_ref++;
-            }
+            Ax[lane] = __dadd_rn(__dadd_rn(__dmul_rn(Q->c, lv[0]), __dmul_rn(-Q->s, lv[1])), Q->x);
+            Ay[lane] = __dadd_rn(__dadd_rn(__dmul_rn(Q->s, lv[0]), __dmul_rn(Q->c, lv[1])), Q->y);
         }
-        // inside/outside of an occupancy centre, exact: the warp shares the segment loop of each such item
-        unsigned todo = __ballot_sync(FULL, have && kind == KIND_PARITY);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const double bx = __shfl_sync(FULL, cx, src), by = __shfl_sync(FULL, cy, src);
-            const int b0 = __shfl_sync(FULL, g0, src), b1 = __shfl_sync(FULL, g1, src);
+        bool collide = false;
+        if (kind == KIND_OBST) {
+            const int nB = p.ob_nv[obj];
+            if ((int)lane < nB) {
+                const double *bv = p.ob_v64 + ((size_t)obj * p.ob_vmax + lane) * 2;
+                Bx[lane] = bv[0]; By[lane] = bv[1];
+            }
+            __syncwarp();
+            // an edge separates iff none of the other polygon's vertices is on its inner side (strict: or on it)
+            unsigned badA = 0, badB = 0;       // bit e set: edge e of A (of B) does not separate
+            for (int c = lane; c < ((nA * nB + 31) & ~31); c += 32) {
+                bool bad = false, bad2 = false;
+                int ea = 0, eb = 0;
+                if (c < nA * nB) {
+                    ea = c / nB;
+                    const int k = c - ea * nB, e1 = (ea + 1 == nA) ? 0 : ea + 1;
+                    if (Ax[ea] == Ax[e1] && Ay[ea] == Ay[e1]) bad = true;
+                    else {
+                        const int o = orient2d(Ax[ea], Ay[ea], Ax[e1], Ay[e1], Bx[k], By[k], ties);
+                        bad = strict ? (o >= 0) : (o > 0);
+                    }
+                    eb = c / nA;
+                    const int k2 = c - eb * nA, f1 = (eb + 1 == nB) ? 0 : eb + 1;
+                    if (Bx[eb] == Bx[f1] && By[eb] == By[f1]) bad2 = true;
+                    else {
+                        const int o = orient2d(Bx[eb], By[eb], Bx[f1], By[f1], Ax[k2], Ay[k2], ties);
+                        bad2 = strict ? (o >= 0) : (o > 0);
+                    }
+                }
+                badA |= __reduce_or_sync(FULL, bad ? (1u << ea) : 0u);
+                badB |= __reduce_or_sync(FULL, bad2 ? (1u << eb) : 0u);
+            }
+            const bool sepA = (~badA & ((1u << nA) - 1u)) != 0, sepB = (~badB & ((1u << nB) - 1u)) != 0;
+            collide = !(sepA || sepB);
+            // near-tangent statistic: |separation| < 1e-9 m, one edge per lane
+            double mine = -1e300;
+            if ((int)lane < nA + nB) {
+                const bool fromA = (int)lane < nA;
+                const int ee = fromA ? lane : lane - nA, nn = fromA ? nA : nB, e1 = (ee + 1 == nn) ? 0 : ee + 1;
+                const double *Px = fromA ? Ax : Bx, *Py = fromA ? Ay : By, *Qx = fromA ? Bx : Ax, *Qy = fromA ? By : Ay;
+                const int nq = fromA ? nB : nA;
+                const double ex = Px[e1] - Px[ee], ey = Py[e1] - Py[ee], len = sqrt(ex * ex + ey * ey);
+                if (len > 0.0) {
+                    double mn = 1e300;
+                    for (int k = 0; k < nq; k++) mn = fmin(mn, ey * (Qx[k] - Px[ee]) - ex * (Qy[k] - Py[ee]));
+                    mine = mn / len;
+                }
+            }
+            for (int o = 16; o; o >>= 1) mine = fmax(mine, __shfl_xor_sync(FULL, mine, o));
+            if (lane == 0) { if (fabs(mine) < 1e-9) near_t++; refined++; }
+        } else if (kind == KIND_SEG) {
+            __syncwarp();
+            const double *sg = p.sg_64 + 4 * (size_t)obj;
+            const double s0x = sg[0], s0y = sg[1], s1x = sg[2], s1y = sg[3];
+            // lanes 0..nA-1: edge i of the polygon against both end points; lanes 16..16+nA-1: vertex against the line
+            bool excl = false, pos = false, neg = false;
+            if ((int)lane < nA) {
+                const int i = lane, k = (i + 1 == nA) ? 0 : i + 1;
+                if (!(Ax[i] == Ax[k] && Ay[i] == Ay[k]))
+                    excl = orient2d(Ax[i], Ay[i], Ax[k], Ay[k], s0x, s0y, ties) <= 0 &&
+                           orient2d(Ax[i], Ay[i], Ax[k], Ay[k], s1x, s1y, ties) <= 0;
+            } else if (lane >= 16 && (int)lane - 16 < nA) {
+                const int o = orient2d(s0x, s0y, s1x, s1y, Ax[lane - 16], Ay[lane - 16], ties);
+                pos = o > 0; neg = o < 0;
+            }
+            const bool any_excl = __any_sync(FULL, excl), any_pos = __any_sync(FULL, pos), any_neg = __any_sync(FULL, neg);
+            const bool point = (s0x == s1x && s0y == s1y);
+            collide = !any_excl && (point || (any_pos && any_neg));
+            if (lane == 0) refined++;
+        } else {
+            __syncwarp();
+            double cx = 0.0, cy = 0.0;
+            for (int k = 0; k < nA; k++) { cx += Ax[k]; cy += Ay[k]; }
+            cx /= nA; cy /= nA;
+            const int step = Q->step0 + Q->t0 + p.slot_t[j];
+            const int g0 = p.step_seg_begin[step], g1 = p.step_seg_end[step];
             bool inside = false, on_edge = false;
-            for (int g = b0 + (int)lane; g < b1; g += 32) {
+            for (int g = g0 + (int)lane; g < g1; g += 32) {
                 const double *sg = p.sg_64 + 4 * (size_t)g;
                 const double sax = sg[0], say = sg[1], sbx = sg[2], sby = sg[3];
                 if (sax == sbx && say == sby) continue;
-                int o = orient2d(sax, say, sbx, sby, bx, by, ties);
-                if (o == 0 && fmin(sax, sbx) <= bx && bx <= fmax(sax, sbx) && fmin(say, sby) <= by && by <= fmax(say, sby))
+                const int o = orient2d(sax, say, sbx, sby, cx, cy, ties);
+                if (o == 0 && fmin(sax, sbx) <= cx && cx <= fmax(sax, sbx) && fmin(say, sby) <= cy && cy <= fmax(say, sby))
                     on_edge = true;
-                if ((say > by) != (sby > by)) {
+                if ((say > cy) != (sby > cy)) {
                     if ((sby > say && o > 0) || (sby < say && o < 0)) inside = !inside;
                 }
             }
             const unsigned odd = __popc(__ballot_sync(FULL, inside)) & 1u;
-            const bool edge = __any_sync(FULL, on_edge);
-            if ((int)lane == src) collide = edge || !odd;
+            collide = __any_sync(FULL, on_edge) || !odd;
+            if (lane == 0) par_ref++;
         }
-        if (have && collide) atomicOr(p.mask + Q->mask_off + (ci >> 5), 1u << (ci & 31));
+        if (lane == 0 && collide) atomicOr(p.mask + Q->mask_off + (ci >> 5), 1u << (ci & 31));
     }
     refined = __reduce_add_sync(FULL, refined);
     ties = __reduce_add_sync(FULL, ties);
@@ -1127,7 +1171,6 @@ extern "C" int mpc_upload_library(mpc_ctx *ctx, const double *verts, const int32
     }
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->P = P; ctx->J = J; ctx->lib_vmax = VA; ctx->VA = VA; ctx->lib_radius = radius; ctx->lib_rmax = rmax;
-    invalidate_graphs(ctx);
     ctx->have_lib = true;
     ctx->prepared = false;
     ctx->arena_valid = false;
@@ -1291,7 +1334,6 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     ctx->ob_vmax = VB; ctx->VB = VB; ctx->max_obst_step = max_o; ctx->max_seg_step = max_s;
     ctx->scene_step_off.assign(scene_step_off, scene_step_off + nscenes + 1);
     ctx->origins.assign(origins, origins + 2 * (size_t)nscenes);
-    invalidate_graphs(ctx);
     ctx->have_scenes = true;
     ctx->prepared = false;
     return MPC_OK;
@@ -1360,7 +1402,7 @@ static int launch_all(mpc_ctx *ctx, cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t 
     if (e1) CU(cudaEventRecord(e1, st));
     CU(launch_check(ctx, p));
     if (e2) CU(cudaEventRecord(e2, st));
-    k_refine<<<std::max(1, ctx->prop.multiProcessorCount), 128, 0, st>>>(p);
+    k_refine<<<std::max(1, ctx->prop.multiProcessorCount) * 8, 128, 0, st>>>(p);     // one warp per item, 32 warps/SM
     CU(cudaGetLastError());
     return MPC_OK;
 }
@@ -1537,7 +1579,9 @@ static int run_graph(mpc_ctx *ctx, float *ms, bool timed) {
     std::vector<long long> key = {(long long)ctx->B, (long long)ctx->ctas, (long long)ctx->mask_words, (long long)ctx->mode,
                                   (long long)ctx->gpc, (long long)ctx->cap_o, (long long)ctx->cap_s, (long long)ctx->smem,
                                   (long long)ctx->up_bytes, (long long)ctx->up_cand_bytes, (long long)ctx->wl_cap,
-                                  (long long)ctx->VA, (long long)ctx->VB};
+                                  (long long)ctx->VA, (long long)ctx->VB, (long long)ctx->ob_stride, (long long)ctx->sg_stride,
+                                  (long long)ctx->ob_vmax, (long long)ctx->P, (long long)ctx->J, (long long)ctx->lib_vmax,
+                                  (long long)__builtin_bit_cast(unsigned, ctx->lib_rmax), (long long)ctx->set_total};
     auto it = ctx->graphs.find(key);
     if (it == ctx->graphs.end()) {
         if (ctx->graphs.size() > 256) invalidate_graphs(ctx);
