@@ -9,18 +9,22 @@
 // the error-band argument and the roofline; include/mpc.h for the ABI.
 //
 // Kernel structure (B200-first, nothing here is derived from reference code -- it has no kernel):
-//   k_stage_obst / k_stage_segs   float64 global-frame inputs -> scene-local float32 SoA records (vertices, unit edge
-//                                 normals, bounding circle), CCW-normalised float64 copy for the tie-break pass.
-//   k_check<VA,VB>                one CTA per (query, occupancy slot, chunk of candidate groups).  The obstacle and
-//                                 boundary-segment records of that time step are brought into shared memory with one
-//                                 TMA bulk copy per field (cp.async.bulk + mbarrier).  One warp works on 32 candidate
-//                                 primitives at a time, lane = primitive: the lane holds its transformed occupancy
-//                                 polygon (vertices + edge lines) in registers and streams the step's obstacles from
-//                                 shared memory as warp-wide broadcasts.  Axis 0 is the centre line with bounding
-//                                 radii; pairs it cannot separate run the full separating-axis test.  A tile ends as
-//                                 soon as __all_sync says every lane has collided; __ballot_sync assembles the 32
-//                                 result bits that are OR-ed into the packed mask.
-//   k_refine                      float64 / exact re-decision of the pairs inside the float32 error band.
+//   k_stage_obst / k_stage_segs   float64 global-frame inputs -> scene-local float32 SoA records (vertex pairs, unit
+//                                 edge lines, quad-packed bounding circles, one box per block of 32 segments) in
+//                                 32-aligned slot ranges per time step; CCW-normalised float64 copy for the tie-break.
+//   k_check<VA,VB,COUNT,NOCULL>   one CTA (8 warps) per (query, occupancy slot, chunk of candidate groups).  The
+//                                 obstacle and boundary-segment records of that time step are brought into shared
+//                                 memory with one TMA bulk copy per field (cp.async.bulk + mbarrier).  A warp works on
+//                                 32 candidate primitives at a time, lane = primitive: it transforms the occupancy
+//                                 polygons, parks them in shared memory and streams the step's obstacles as
+//                                 warp-broadcast loads.  Axis 0 (centre line, bounding radii) runs on packed
+//                                 FADD2/FFMA2, two obstacles per instruction; the pairs it cannot separate are queued
+//                                 per warp and the full separating-axis test runs on 32 queued pairs at once.  A tile
+//                                 ends as soon as __all_sync says every lane has collided; __ballot_sync assembles the
+//                                 32 result bits that are OR-ed into the packed mask.
+//   k_refine                      float64 / exact re-decision of the pairs inside the float32 error band, one warp per
+//                                 pair (lanes over the orientation tests).
+// mpc_query replays the sequence (H2D, clear, k_check, k_refine, D2H) as one instantiated CUDA graph per batch shape.
 #include <cuda_runtime.h>
 
 #include <algorithm>
