@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--queries", type=int, default=16, help="queries (ego poses) per step")
-    ap.add_argument("--ref-queries", type=int, default=4, help="queries per step of the CPU reference arm")
+    ap.add_argument("--ref-queries", type=int, default=2, help="queries per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
