@@ -73,6 +73,7 @@ typedef struct {
     int64_t cull_tests;       /* MPC_MODE_COUNT_WORK: bounding-circle axis evaluations                             */
     int64_t axis_tests;       /* MPC_MODE_COUNT_WORK: full separating-axis evaluations (pairs that passed the cull)*/
     int64_t worklist_overflow;/* 1 if the refinement list had to be grown and the query was re-run                 */
+    int64_t box_skipped;      /* MPC_MODE_COUNT_WORK: pairs separated wholesale by a block bounding box            */
     float tau;                /* float32 uncertainty band used (metres)                                            */
     float ms_device;          /* device time of the kernels of this call (CUDA events on the context's stream)     */
     int32_t ctas;             /* thread blocks of the main kernel                                                  */

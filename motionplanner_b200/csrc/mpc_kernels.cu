@@ -55,11 +55,13 @@ struct QDev {
     float lx, ly, lc, ls;         // float32 pose relative to the scene origin
     int step0, nsteps, t0, step_limit;
     int cand_base, cand_cnt, mask_off, chunks;
+    int pos_base, pad0, pad1, pad2;   // >= 0: candidates are a spatially sorted set, cand_pos[pos_base + i] = original slot
 };
 
 struct Counters {
     unsigned long long pairs_nominal, refined, exact_ties, near_tangent, parity_refined, cull_tests, axis_tests;
     unsigned wl_count, pad;
+    unsigned long long box_skipped, pad1[7];
 };
 
 struct KParams {
@@ -70,6 +72,7 @@ struct KParams {
     int PJ, J, lib_vmax;
     // scenes
     const float4 *ob_f;          // [F-1][ob_stride] vertex and edge-line fields, slot layout (steps 32-aligned)
+    const float4 *ob_box;        // [ob_stride/32] bounding box of the circles of every block of 32 slots
     const float *ob_c;           // [3][ob_stride]   bounding circle x | y | r, slot layout
     const double *ob_v64;
     const int *ob_nv;
@@ -81,9 +84,10 @@ struct KParams {
     const float *maxabs_scene;
     // queries
     const QDev *q;
-    const int *cta_off, *cand;
-    int B;
-    unsigned *mask;
+    const int *cta_off, *cand, *cand_pos;
+    int B, nwords;
+    unsigned *mask;              // result bits, caller's candidate order
+    unsigned *mask_sorted;       // result bits of spatially sorted candidate sets, un-permuted by k_refine
     int4 *wl;
     int wl_cap;
     Counters *cnt;
@@ -163,23 +167,102 @@ __device__ __forceinline__ void atomic_max_pos_float(float *addr, float v) {
     atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
 }
 
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+__device__ __forceinline__ unsigned morton16_dev(unsigned x, unsigned y) {
+    auto spread = [](unsigned v) {
+        v &= 0xffff;
+        v = (v | (v << 8)) & 0x00ff00ff;
+        v = (v | (v << 4)) & 0x0f0f0f0f;
+        v = (v | (v << 2)) & 0x33333333;
+        v = (v | (v << 1)) & 0x55555555;
+        return v;
+    };
+    return spread(x) | (spread(y) << 1);
+}
+
+// One CTA per time step: order the step's obstacles along a Morton curve (keys from the vertex mean relative to the
+// scene origin, 6 cm cells over +-2 km) with a bitonic sort in shared memory, so that a block of 32 consecutive slots
+// is spatially compact and k_check can skip it by its bounding box.  order[slot] = source obstacle (or -1: padding).
+// Steps with more than SORT_MAX obstacles keep their input order (the boxes are then just less selective).
+constexpr int SORT_MAX = 2048;
+template <int VB>
+__global__ void __launch_bounds__(256) k_order_obst(const double *__restrict__ src64, const int *__restrict__ src_nv,
+                                                    const int *__restrict__ src_off, const int *__restrict__ slot_off,
+                                                    const int *__restrict__ scene_step_off, int nscenes,
+                                                    const double *__restrict__ origins, int *__restrict__ order) {
+    __shared__ unsigned s_key[SORT_MAX];
+    __shared__ int s_idx[SORT_MAX];
+    const int step = blockIdx.x;
+    const int o0 = src_off[step], cnt = src_off[step + 1] - o0, s0 = slot_off[step], nslot = slot_off[step + 1] - s0;
+    if (cnt > SORT_MAX) {
+        for (int i = threadIdx.x; i < nslot; i += blockDim.x) order[s0 + i] = (i < cnt) ? o0 + i : -1;
+        return;
+    }
+    int n2 = 32;
+    while (n2 < cnt) n2 <<= 1;
+    const int sc = upper_bound_idx(scene_step_off, nscenes + 1, step);
+    const double ox = origins[2 * sc], oy = origins[2 * sc + 1];
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        unsigned key = 0xffffffffu;
+        if (i < cnt) {
+            const int nv = src_nv[o0 + i];
+            const double *v = src64 + (size_t)(o0 + i) * VB * 2;
+            double cx = 0.0, cy = 0.0;
+            for (int k = 0; k < nv && k < VB; k++) { cx += v[2 * k]; cy += v[2 * k + 1]; }
+            if (nv > 0) { cx = cx / nv - ox; cy = cy / nv - oy; }
+            const double qx = fmin(fmax((cx + 2048.0) * 16.0, 0.0), 65535.0), qy = fmin(fmax((cy + 2048.0) * 16.0, 0.0), 65535.0);
+            key = morton16_dev((unsigned)qx, (unsigned)qy);
+            if (key == 0xffffffffu) key = 0xfffffffeu;
+        }
+        s_key[i] = key;
+        s_idx[i] = (i < cnt) ? o0 + i : -1;
+    }
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                const int l = i ^ jj;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const unsigned a = s_key[i], b = s_key[l];
+                    // ties are broken by the source index so that the order is deterministic
+                    const bool gt = a > b || (a == b && s_idx[i] > s_idx[l]);
+                    if (gt == up) {
+                        s_key[i] = b; s_key[l] = a;
+                        const int t = s_idx[i]; s_idx[i] = s_idx[l]; s_idx[l] = t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < nslot; i += blockDim.x) order[s0 + i] = (i < cnt) ? s_idx[i] : -1;
+}
+
 // one thread per obstacle *slot*: the obstacles of a step occupy a 32-aligned slot range [slot_off[k], slot_off[k+1]),
 // the tail is padding that can never be near anything.  Writes the float32 SoA records, the bounding circle arrays and
 // the CCW-normalised float64 copy (slot layout) for the tie-break pass.
 template <int VB>
 __global__ void k_stage_obst(int nslots, const double *__restrict__ src64, const int *__restrict__ src_nv,
-                             const int *__restrict__ src_off, const int *__restrict__ slot_off, int nsteps,
+                             const int *__restrict__ order, const int *__restrict__ slot_off, int nsteps,
                              const int *__restrict__ scene_step_off, int nscenes, const double *__restrict__ origins,
-                             float4 *__restrict__ ob_f, float *__restrict__ ob_c, double *__restrict__ ob64,
-                             int *__restrict__ ob_nv, int stride, float *maxabs) {
-    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+                             float4 *__restrict__ ob_f, float *__restrict__ ob_c, float4 *__restrict__ ob_box,
+                             double *__restrict__ ob64, int *__restrict__ ob_nv, int stride, float *maxabs) {
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;     // nslots is a multiple of 32: whole warps are in range
     if (slot >= nslots) return;
     constexpr int F = ob_fields(VB);
     const int step = upper_bound_idx(slot_off, nsteps + 1, slot);
-    const int local = slot - slot_off[step];
-    const int cnt = src_off[step + 1] - src_off[step];
-    const int o = src_off[step] + local;
-    int nv = (local < cnt) ? src_nv[o] : 0;
+    const int o = order[slot];
+    int nv = (o >= 0) ? src_nv[o] : 0;
     float out[F * 4];
     float ccx = FAR, ccy = FAR, ccr = 0.f;
     double *v = ob64 + (size_t)slot * VB * 2;
@@ -252,17 +335,13 @@ __global__ void k_stage_obst(int nslots, const double *__restrict__ src64, const
     ob_c[slot] = ccx;
     ob_c[(size_t)stride + slot] = ccy;
     ob_c[(size_t)2 * stride + slot] = ccr;
-}
-
-__device__ __forceinline__ float warp_min(float v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
-    return v;
+    // bounding box of the block's circles (of the float32 values the main kernel will see)
+    const bool real = nv > 0;
+    const float x0 = warp_min(real ? ccx - ccr : BIG), x1 = warp_max(real ? ccx + ccr : -BIG);
+    const float y0 = warp_min(real ? ccy - ccr : BIG), y1 = warp_max(real ? ccy + ccr : -BIG);
+    if ((threadIdx.x & 31) == 0)
+        ob_box[slot >> 5] = make_float4(__fadd_rd(x0, -1e-6f * fabsf(x0)), __fadd_rd(y0, -1e-6f * fabsf(y0)),
+                                        __fadd_ru(x1, 1e-6f * fabsf(x1)), __fadd_ru(y1, 1e-6f * fabsf(y1)));
 }
 
 // one thread per segment slot (slots are laid out in 32-aligned, spatially sorted ranges by the host); a warp = one
@@ -412,7 +491,22 @@ __global__ void __launch_bounds__(K_THREADS, 4) k_check(const KParams p) {
     const unsigned lt_mask = (1u << lane) - 1u;
 
     // which (query, slot, chunk) is this CTA
-    int q = upper_bound_idx(p.cta_off, p.B + 1, (int)blockIdx.x);
+    // (largest q with cta_off[q] <= blockIdx.x; every warp finds it with warp-wide loads and votes instead of a
+    // chain of dependent loads: a 32-way search per round)
+    int q = 0;
+    {
+        int lo = 0, hi = p.B + 1;                 // answer in [lo, hi)
+        while (hi - lo > 1) {
+            const int span = hi - lo, stride = (span + 31) >> 5;
+            const int idx = lo + lane * stride;
+            const bool le = idx < hi && __ldg(p.cta_off + idx) <= (int)blockIdx.x;
+            const int k = __popc(__ballot_sync(FULL, le));       // cta_off is sorted: the first k probes are <=
+            const int nlo = lo + (k - 1) * stride;
+            hi = min(hi, nlo + stride);
+            lo = nlo;
+        }
+        q = lo;
+    }
     const QDev *Q = p.q + q;
     int local = blockIdx.x - p.cta_off[q];
     int chunks = Q->chunks;
@@ -442,7 +536,8 @@ __global__ void __launch_bounds__(K_THREADS, 4) k_check(const KParams p) {
     const int nphase = max(1, max(nph_o, nph_s));
     // cull radius shared by the whole CTA: largest library bounding radius + band (conservative for smaller polygons)
     const float rcull = p.lib_rmax + 2.0f * tau;
-    unsigned n_cull = 0, n_axis = 0;
+    unsigned n_cull = 0, n_axis = 0, n_skip = 0;
+    const int pos_base = Q->pos_base;
     float4 *sA = s_A + warp * FA * 32;
     unsigned *sq = s_q + warp * QCAP;
 
@@ -471,12 +566,27 @@ __global__ void __launch_bounds__(K_THREADS, 4) k_check(const KParams p) {
             }
             __syncthreads();
         }
+        // candidate index of the warp's first group; the next group's is fetched
+        // while the current one is processed, which takes one link out of the dependent-load chain of the set-up
+        int nxt_prim = 0;
+        {
+            const int ci0 = (gbeg + warp) * 32 + lane;
+            if (warp < ng && ci0 < cand_cnt) {
+                nxt_prim = __ldg(p.cand + cand_base + ci0);
+            }
+        }
         for (int g = warp; g < ng; g += NW) {
             // ---- lane = one candidate primitive: transform its occupancy polygon, park it in shared memory ----------
             const int ci = (gbeg + g) * 32 + lane;
             bool active = ci < cand_cnt;
             int pj = 0;
-            if (active) pj = p.cand[cand_base + ci] * p.J + j;
+            if (active) pj = nxt_prim * p.J + j;
+            {
+                const int cin = ci + NW * 32;
+                if (g + NW < ng && cin < cand_cnt) {
+                    nxt_prim = __ldg(p.cand + cand_base + cin);
+                }
+            }
             float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
             if (active) cc = __ldg(p.lib_c + pj);
             const int nv = (int)cc.w;
@@ -516,6 +626,15 @@ __global__ void __launch_bounds__(K_THREADS, 4) k_check(const KParams p) {
             bool collide = (s_coll[g] >> lane) & 1u;
             bool par = false, punc = false;
             unsigned qn = 0;                        // entries in this warp's queue (warp-uniform)
+            // bounding box of the warp's 32 polygon centres: decides which 32-blocks of the spatially sorted obstacle
+            // slots / boundary segments can matter for anyone in the warp
+            const bool cull_o = !NOCULL && nslot > 32, cull_s = !NOCULL && nseg > 32;
+            float wx0 = 0.f, wx1 = 0.f, wy0 = 0.f, wy1 = 0.f, wr = 0.f;
+            if (cull_o || cull_s) {
+                wx0 = warp_min(active ? acx : BIG); wx1 = warp_max(active ? acx : -BIG);
+                wy0 = warp_min(active ? acy : BIG); wy1 = warp_max(active ? acy : -BIG);
+                wr = warp_max(active ? arr : 0.f);
+            }
 
             if (ph == 0) {   // statistic: nominal pair count of this tile
                 unsigned w = __reduce_add_sync(FULL, active ? (unsigned)(nobst + nseg) : 0u);
@@ -607,7 +726,24 @@ __global__ void __launch_bounds__(K_THREADS, 4) k_check(const KParams p) {
                 const float4 *s_cy4 = reinterpret_cast<const float4 *>(s_c + p.cap_o);
                 const float4 *s_cr4 = reinterpret_cast<const float4 *>(s_c + 2 * p.cap_o);
                 const f32x2 nax = pack2(-acx, -acx), nay = pack2(-acy, -acy);
+                // which blocks of 32 slots can matter: lane b tests block b (one load latency for the whole tile).  A
+                // block whose circles (box already inflated by their radii) cannot come within rcull of any centre of
+                // this warp has every pair separated on the box axis.
+                unsigned live_o = FULL;
+                if (cull_o) {
+                    const int nblk = ocn >> 5;               // <= 10 (cap_o <= 320)
+                    bool live = false;
+                    if (lane < nblk) {
+                        const float4 bb = __ldg(p.ob_box + ((o0 + oc0) >> 5) + lane);
+                        live = !(bb.x > wx1 + rcull || bb.z < wx0 - rcull || bb.y > wy1 + rcull || bb.w < wy0 - rcull);
+                    }
+                    live_o = __ballot_sync(FULL, live);
+                }
                 for (int ob = 0; ob < ocn; ob += 32) {
+                    if (!((live_o >> (ob >> 5)) & 1u)) {
+                        if (COUNT && active) n_skip += min(32, nobst - oc0 - ob);
+                        continue;
+                    }
                     // axis 0: centre line with bounding radii.  Three warp-broadcast LDS.128 bring four obstacles; packed
                     // FADD2/FFMA2 evaluate e = |dc|^2 - (rb + rcull)^2 for two of them per instruction and the sign bit
                     // of e is shifted into the hit word (bit 31-k <-> slot ob+k).
@@ -637,15 +773,7 @@ __global__ void __launch_bounds__(K_THREADS, 4) k_check(const KParams p) {
 
             // ---- boundary segments of the free space at this time step -----------------------------------------
             if (scn && (noexit || !__all_sync(FULL, collide || !active))) {
-                // bounding box of the warp's 32 polygon centres and their largest radius: decides which 32-blocks of
-                // the (spatially sorted) segment range can matter for anyone in the warp
-                const bool blockcull = !NOCULL && nseg > 32;      // a single block cannot be skipped: no box work
-                float wx0 = 0.f, wx1 = 0.f, wy0 = 0.f, wy1 = 0.f, wr = 0.f;
-                if (blockcull) {
-                    wx0 = warp_min(active ? acx : BIG); wx1 = warp_max(active ? acx : -BIG);
-                    wy0 = warp_min(active ? acy : BIG); wy1 = warp_max(active ? acy : -BIG);
-                    wr = warp_max(active ? arr : 0.f);
-                }
+                const bool blockcull = cull_s;        // a single block cannot be skipped: no box work
                 const float4 *boxes = p.sg_box + ((g0 + sc0) >> 5);
                 // the even-odd ray may run along +x, -x, +y or -y; take the direction whose ray corridor meets the
                 // fewest blocks of the whole range (a road aligned with the ray would otherwise keep every block alive)
@@ -669,18 +797,25 @@ __global__ void __launch_bounds__(K_THREADS, 4) k_check(const KParams p) {
                 }
                 const bool ray_y = dir >= 2, flip = (dir == 1) || (dir == 2);
                 const float pc = ray_y ? acx : acy;          // coordinate the ray keeps constant
-                for (int sb = 0; sb < scn; sb += 32) {
-                    const int cnt = min(32, scn - sb);
-                    if (blockcull) {
-                        const float4 bb = __ldg(boxes + (sb >> 5));
+                // live blocks of this phase (<= 16: cap_s <= 512), lane b tests block b
+                unsigned live_s = FULL;
+                if (blockcull) {
+                    bool live = false;
+                    if (lane < ((scn + 31) >> 5)) {
+                        const float4 bb = __ldg(boxes + lane);
                         // a segment can meet a polygon only if the boxes overlap; it can be crossed by the ray of a
                         // centre only if it reaches that centre's constant coordinate and is not entirely behind it
                         const bool sat_rel = bb.x <= wx1 + wr && bb.z >= wx0 - wr && bb.y <= wy1 + wr && bb.w >= wy0 - wr;
                         const bool iny = bb.w >= wy0 && bb.y <= wy1, inx = bb.z >= wx0 && bb.x <= wx1;
                         const bool par_rel = dir == 0 ? (iny && bb.z >= wx0) : dir == 1 ? (iny && bb.x <= wx1)
                                            : dir == 2 ? (inx && bb.w >= wy0) : (inx && bb.y <= wy1);
-                        if (!sat_rel && !par_rel) continue;
+                        live = sat_rel || par_rel;
                     }
+                    live_s = __ballot_sync(FULL, live);
+                }
+                for (int sb = 0; sb < scn; sb += 32) {
+                    const int cnt = min(32, scn - sb);
+                    if (!((live_s >> (sb >> 5)) & 1u)) continue;
                     unsigned hits = 0;
 #pragma unroll 2
                     for (int k = 0; k < cnt; k++) {
@@ -720,8 +855,13 @@ __global__ void __launch_bounds__(K_THREADS, 4) k_check(const KParams p) {
                     if ((bu >> lane) & 1u) push_work(p, q, ci, j, KIND_PARITY, 0);
                     else if (!((bp >> lane) & 1u)) coll = true;        // centre outside the region
                 }
-                unsigned word = __ballot_sync(FULL, coll && active);
-                if (lane == 0 && word) atomicOr(p.mask + Q->mask_off + gbeg + g, word);
+                if (pos_base < 0) {
+                    unsigned word = __ballot_sync(FULL, coll && active);
+                    if (lane == 0 && word) atomicOr(p.mask + Q->mask_off + gbeg + g, word);
+                } else {        // spatially sorted candidate set: bits in sorted order, k_refine moves them home
+                    unsigned word = __ballot_sync(FULL, coll && active);
+                    if (lane == 0 && word) atomicOr(p.mask_sorted + Q->mask_off + gbeg + g, word);
+                }
             }
         }
         if (nphase > 1) __syncthreads();      // everyone is done with the tile before the next bulk copy overwrites it
@@ -729,9 +869,11 @@ __global__ void __launch_bounds__(K_THREADS, 4) k_check(const KParams p) {
     if (COUNT) {
         n_cull = __reduce_add_sync(FULL, n_cull);
         n_axis = __reduce_add_sync(FULL, n_axis);
+        n_skip = __reduce_add_sync(FULL, n_skip);
         if (lane == 0) {
             atomicAdd(&p.cnt->cull_tests, (unsigned long long)n_cull);
             atomicAdd(&p.cnt->axis_tests, (unsigned long long)n_axis);
+            atomicAdd(&p.cnt->box_skipped, (unsigned long long)n_skip);
         }
     }
 }
@@ -751,6 +893,26 @@ __global__ void __launch_bounds__(128) k_refine(const KParams p) {
     double *Ax = s_pts[wib], *Ay = Ax + MPC_MAX_LIB_VERTS, *Bx = Ay + MPC_MAX_LIB_VERTS, *By = Bx + MPC_MAX_OBST_VERTS;
     unsigned refined = 0, ties = 0, near_t = 0, par_ref = 0;
     const bool strict = p.mode & MPC_MODE_VALIDATOR;
+    // phase A: result bits of spatially sorted candidate sets go home to the caller's candidate order: one thread per
+    // mask word (its query found by bisection on the mask offsets), only set bits cost an atomic
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < p.nwords; w += gridDim.x * blockDim.x) {
+        unsigned bits = p.mask_sorted[w];
+        if (!bits) continue;
+        int lo = 0, hi = p.B;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (p.q[mid].mask_off <= w) lo = mid; else hi = mid;
+        }
+        while (lo + 1 < p.B && p.q[lo + 1].mask_off <= w) lo++;          // queries without candidates share an offset
+        const QDev *Q = p.q + lo;
+        const int base = Q->pos_base + (w - Q->mask_off) * 32;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int oi = __ldg(p.cand_pos + base + b);
+            atomicOr(p.mask + Q->mask_off + (oi >> 5), 1u << (oi & 31));
+        }
+    }
     for (unsigned item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n; item += warps) {
         const int4 e = p.wl[item];
         const int q = e.x, ci = e.y, j = e.z & 0xffff, kind = e.z >> 16, obj = e.w;
@@ -856,7 +1018,10 @@ __global__ void __launch_bounds__(128) k_refine(const KParams p) {
             collide = __any_sync(FULL, on_edge) || !odd;
             if (lane == 0) par_ref++;
         }
-        if (lane == 0 && collide) atomicOr(p.mask + Q->mask_off + (ci >> 5), 1u << (ci & 31));
+        if (lane == 0 && collide) {
+            const int oi = Q->pos_base >= 0 ? p.cand_pos[Q->pos_base + ci] : ci;
+            atomicOr(p.mask + Q->mask_off + (oi >> 5), 1u << (oi & 31));
+        }
     }
     refined = __reduce_add_sync(FULL, refined);
     ties = __reduce_add_sync(FULL, ties);
@@ -906,7 +1071,7 @@ struct mpc_ctx {
     int nscenes = 0, nsteps = 0, nobst = 0, nseg = 0, ob_vmax = 4, VB = 4, max_obst_step = 0, max_seg_step = 0;
     std::vector<int> scene_step_off;
     std::vector<double> origins;
-    DevBuf ob_src, ob_src_nv, ob_src_off, ob_c, step_obst_cnt;
+    DevBuf ob_src, ob_src_nv, ob_src_off, ob_c, ob_box, ob_order, step_obst_cnt, sets_pos;
     int ob_stride = 32;
     DevBuf ob_in, ob_f, ob_nv, step_obst_off, step_seg_begin, step_seg_end, scene_step_off_d, origins_d, sg_64, sg_f,
         sg_box, seg_scene, maxabs;
@@ -957,7 +1122,7 @@ static cudaError_t ensure(mpc_ctx *ctx, DevBuf &b, size_t bytes) {
     if (b.p) cudaFree(b.p);
     b.p = nullptr;
     b.cap = 0;
-    size_t want = std::max<size_t>(bytes + bytes / 4, 256);
+    size_t want = std::max<size_t>(bytes + bytes / 4, (size_t)1 << 18);   // generous floor: reallocations stall the stream
     cudaError_t e = cudaMalloc(&b.p, want);
     if (e == cudaSuccess) b.cap = want;
     return e;
@@ -1019,7 +1184,8 @@ extern "C" void mpc_destroy(mpc_ctx *ctx) {
         cudaStreamSynchronize(ctx->stream);
     }
     DevBuf *bufs[] = {&ctx->lib_v, &ctx->lib_n, &ctx->lib_c, &ctx->lib_v64, &ctx->lib_nv, &ctx->slot_t, &ctx->sets,
-                      &ctx->ob_src, &ctx->ob_src_nv, &ctx->ob_src_off, &ctx->ob_c, &ctx->step_obst_cnt,
+                      &ctx->ob_src, &ctx->ob_src_nv, &ctx->ob_src_off, &ctx->ob_c, &ctx->ob_box, &ctx->ob_order, &ctx->step_obst_cnt,
+                      &ctx->sets_pos,
                       &ctx->ob_in, &ctx->ob_f, &ctx->ob_nv, &ctx->step_obst_off, &ctx->step_seg_begin,
                       &ctx->step_seg_end, &ctx->scene_step_off_d, &ctx->origins_d, &ctx->sg_64, &ctx->sg_f,
                       &ctx->sg_box, &ctx->seg_scene, &ctx->maxabs, &ctx->qpack_d, &ctx->cand_d, &ctx->res_d, &ctx->wl,
@@ -1050,6 +1216,18 @@ extern "C" int mpc_device_info(mpc_ctx *ctx, mpc_devinfo *out) {
     out->l2_bytes = ctx->prop.l2CacheSize;
     out->abi_version = MPC_ABI_VERSION;
     return MPC_OK;
+}
+
+static inline unsigned morton16(unsigned x, unsigned y) {
+    auto spread = [](unsigned v) {
+        v &= 0xffff;
+        v = (v | (v << 8)) & 0x00ff00ff;
+        v = (v | (v << 4)) & 0x0f0f0f0f;
+        v = (v | (v << 2)) & 0x33333333;
+        v = (v | (v << 1)) & 0x55555555;
+        return v;
+    };
+    return spread(x) | (spread(y) << 1);
 }
 
 extern "C" int mpc_alloc_pinned(mpc_ctx *ctx, uint64_t bytes, void **out) {
@@ -1170,8 +1348,41 @@ extern "C" int mpc_upload_library(mpc_ctx *ctx, const double *verts, const int32
         ctx->set_off.assign(set_off, set_off + nsets + 1);
         ctx->nsets = nsets;
         ctx->set_total = total;
-        CU(ensure(ctx, ctx->sets, std::max<size_t>(total, 1) * sizeof(int)));
-        if (total) CU(cudaMemcpyAsync(ctx->sets.p, set_idx, (size_t)total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        // every set is kept twice: in the caller's order (sub-ranges of a set) and sorted along a Morton curve of the
+        // primitives' last occupancy centre (whole-set queries): neighbouring lanes then hold neighbouring polygons at
+        // every time step, which is what makes the per-warp block culling of k_check selective.  pos[] maps a sorted
+        // entry back to its slot in the caller's order (that is where its result bit goes).
+        std::vector<int> both((size_t)2 * std::max(total, 1)), pos((size_t)std::max(total, 1));
+        for (int i = 0; i < total; i++) both[i] = set_idx[i];
+        for (int sidx = 0; sidx < nsets; sidx++) {
+            const int b = set_off[sidx], e = set_off[sidx + 1], n = e - b;
+            std::vector<std::pair<float, float>> c(n);
+            float x0 = 1e30f, x1 = -1e30f, y0 = 1e30f, y1 = -1e30f;
+            for (int i = 0; i < n; i++) {
+                const int pr = set_idx[b + i];
+                float cx = 0.f, cy = 0.f;
+                for (int j = J - 1; j >= 0; j--)
+                    if (hnv[(size_t)pr * J + j] > 0) { cx = hc[(size_t)pr * J + j].x; cy = hc[(size_t)pr * J + j].y; break; }
+                c[i] = {cx, cy};
+                x0 = std::min(x0, cx); x1 = std::max(x1, cx); y0 = std::min(y0, cy); y1 = std::max(y1, cy);
+            }
+            const float sx = x1 > x0 ? 65535.f / (x1 - x0) : 0.f, sy = y1 > y0 ? 65535.f / (y1 - y0) : 0.f;
+            std::vector<std::pair<unsigned, int>> order(n);
+            for (int i = 0; i < n; i++)
+                order[i] = {morton16((unsigned)((c[i].first - x0) * sx), (unsigned)((c[i].second - y0) * sy)), i};
+            std::sort(order.begin(), order.end());
+            for (int i = 0; i < n; i++) {
+                both[(size_t)total + b + i] = set_idx[b + order[i].second];
+                pos[b + i] = order[i].second;
+            }
+        }
+        CU(ensure(ctx, ctx->sets, both.size() * sizeof(int)));
+        CU(ensure(ctx, ctx->sets_pos, pos.size() * sizeof(int)));
+        if (total) {
+            CU(cudaMemcpyAsync(ctx->sets.p, both.data(), (size_t)2 * total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->sets_pos.p, pos.data(), (size_t)total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
     }
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->P = P; ctx->J = J; ctx->lib_vmax = VA; ctx->VA = VA; ctx->lib_radius = radius; ctx->lib_rmax = rmax;
@@ -1182,18 +1393,6 @@ extern "C" int mpc_upload_library(mpc_ctx *ctx, const double *verts, const int32
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-static inline unsigned morton16(unsigned x, unsigned y) {
-    auto spread = [](unsigned v) {
-        v &= 0xffff;
-        v = (v | (v << 8)) & 0x00ff00ff;
-        v = (v | (v << 4)) & 0x0f0f0f0f;
-        v = (v | (v << 2)) & 0x33333333;
-        v = (v | (v << 1)) & 0x55555555;
-        return v;
-    };
-    return spread(x) | (spread(y) << 1);
-}
-
 extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_off, const double *origins,
                               const int32_t *step_obst_off, const double *obst, const int32_t *obst_nv, int Vo,
                               const int32_t *step_seg_begin, const int32_t *step_seg_end, const double *segs, int nseg) {
@@ -1286,6 +1485,8 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     CU(ensure(ctx, ctx->ob_nv, (size_t)ob_stride * sizeof(int)));
     CU(ensure(ctx, ctx->ob_f, (size_t)ob_stride * F * sizeof(float4)));
     CU(ensure(ctx, ctx->ob_c, (size_t)ob_stride * 3 * sizeof(float)));
+    CU(ensure(ctx, ctx->ob_box, (size_t)(ob_stride / 32 + 1) * sizeof(float4)));
+    CU(ensure(ctx, ctx->ob_order, (size_t)ob_stride * sizeof(int)));
     CU(ensure(ctx, ctx->sg_64, (size_t)sg_stride * 4 * sizeof(double)));
     CU(ensure(ctx, ctx->sg_f, (size_t)sg_stride * 2 * sizeof(float4)));
     CU(ensure(ctx, ctx->sg_box, (size_t)(sg_stride / 32 + 1) * sizeof(float4)));
@@ -1310,16 +1511,23 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
         }
         CU(cudaMemcpyAsync(ctx->ob_src_nv.p, obst_nv, (size_t)nobst * sizeof(int), cudaMemcpyHostToDevice, st));
         int blocks = (noslots + 127) / 128;
-        if (VB == 4)
-            k_stage_obst<4><<<blocks, 128, 0, st>>>(noslots, (const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_src_off.p,
+        if (VB == 4) {
+            k_order_obst<4><<<nsteps, 256, 0, st>>>((const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_src_off.p,
+                                                    (const int *)ctx->step_obst_off.p, (const int *)ctx->scene_step_off_d.p, nscenes,
+                                                    (const double *)ctx->origins_d.p, (int *)ctx->ob_order.p);
+            k_stage_obst<4><<<blocks, 128, 0, st>>>(noslots, (const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_order.p,
                                                    (const int *)ctx->step_obst_off.p, nsteps, (const int *)ctx->scene_step_off_d.p, nscenes,
-                                                   (const double *)ctx->origins_d.p, (float4 *)ctx->ob_f.p, (float *)ctx->ob_c.p, (double *)ctx->ob_in.p,
-                                                   (int *)ctx->ob_nv.p, ob_stride, (float *)ctx->maxabs.p);
-        else
-            k_stage_obst<8><<<blocks, 128, 0, st>>>(noslots, (const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_src_off.p,
+                                                   (const double *)ctx->origins_d.p, (float4 *)ctx->ob_f.p, (float *)ctx->ob_c.p, (float4 *)ctx->ob_box.p,
+                                                   (double *)ctx->ob_in.p, (int *)ctx->ob_nv.p, ob_stride, (float *)ctx->maxabs.p);
+        } else {
+            k_order_obst<8><<<nsteps, 256, 0, st>>>((const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_src_off.p,
+                                                    (const int *)ctx->step_obst_off.p, (const int *)ctx->scene_step_off_d.p, nscenes,
+                                                    (const double *)ctx->origins_d.p, (int *)ctx->ob_order.p);
+            k_stage_obst<8><<<blocks, 128, 0, st>>>(noslots, (const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_order.p,
                                                    (const int *)ctx->step_obst_off.p, nsteps, (const int *)ctx->scene_step_off_d.p, nscenes,
-                                                   (const double *)ctx->origins_d.p, (float4 *)ctx->ob_f.p, (float *)ctx->ob_c.p, (double *)ctx->ob_in.p,
-                                                   (int *)ctx->ob_nv.p, ob_stride, (float *)ctx->maxabs.p);
+                                                   (const double *)ctx->origins_d.p, (float4 *)ctx->ob_f.p, (float *)ctx->ob_c.p, (float4 *)ctx->ob_box.p,
+                                                   (double *)ctx->ob_in.p, (int *)ctx->ob_nv.p, ob_stride, (float *)ctx->maxabs.p);
+        }
         CU(cudaGetLastError());
     }
     if (nslots) {
@@ -1345,7 +1553,7 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
 
 // ---------------------------------------------------------------------------------------------------------------------
 // result block on the device: [Counters (64 B)] [mask words]; one memset clears it, one copy brings it back
-static_assert(sizeof(Counters) == 64, "Counters is the 64-byte head of the result block");
+static_assert(sizeof(Counters) == 128, "Counters is the 128-byte head of the result block");
 
 static KParams make_params(mpc_ctx *ctx) {
     KParams p;
@@ -1353,7 +1561,7 @@ static KParams make_params(mpc_ctx *ctx) {
     p.lib_v = (const float4 *)ctx->lib_v.p; p.lib_n = (const float4 *)ctx->lib_n.p; p.lib_c = (const float4 *)ctx->lib_c.p;
     p.lib_v64 = (const double *)ctx->lib_v64.p; p.lib_nv = (const int *)ctx->lib_nv.p; p.slot_t = (const int *)ctx->slot_t.p;
     p.PJ = ctx->P * ctx->J; p.J = ctx->J; p.lib_vmax = ctx->lib_vmax;
-    p.ob_f = (const float4 *)ctx->ob_f.p; p.ob_c = (const float *)ctx->ob_c.p;
+    p.ob_f = (const float4 *)ctx->ob_f.p; p.ob_c = (const float *)ctx->ob_c.p; p.ob_box = (const float4 *)ctx->ob_box.p;
     p.ob_v64 = (const double *)ctx->ob_in.p; p.ob_nv = (const int *)ctx->ob_nv.p;
     p.ob_stride = ctx->ob_stride; p.ob_vmax = ctx->ob_vmax;
     p.step_obst_off = (const int *)ctx->step_obst_off.p; p.step_obst_cnt = (const int *)ctx->step_obst_cnt.p;
@@ -1364,8 +1572,11 @@ static KParams make_params(mpc_ctx *ctx) {
     p.maxabs_scene = (const float *)ctx->maxabs.p;
     char *qp = (char *)ctx->qpack_d.p;
     p.q = (const QDev *)qp; p.cta_off = (const int *)(qp + ctx->qpack_cta_off); p.cand = (const int *)ctx->cand_d.p;
+    p.cand_pos = (const int *)ctx->sets_pos.p;
     p.B = ctx->B;
     p.cnt = (Counters *)ctx->res_d.p; p.mask = (unsigned *)((char *)ctx->res_d.p + sizeof(Counters));
+    p.mask_sorted = p.mask + ctx->mask_words;
+    p.nwords = ctx->mask_words;
     p.wl = (int4 *)ctx->wl.p; p.wl_cap = ctx->wl_cap;
     p.maxabs_query = (const float *)(qp + ctx->qpack_hdr_off); p.lib_rmax = ctx->lib_rmax; p.mode = ctx->mode;
     p.gpc = ctx->gpc; p.cap_o = ctx->cap_o; p.cap_s = ctx->cap_s;
@@ -1402,7 +1613,7 @@ static int launch_all(mpc_ctx *ctx, cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t 
     KParams p = make_params(ctx);
     cudaStream_t st = ctx->stream;
     if (e0) CU(cudaEventRecord(e0, st));
-    CU(cudaMemsetAsync(ctx->res_d.p, 0, sizeof(Counters) + (size_t)ctx->mask_words * sizeof(unsigned), st));
+    CU(cudaMemsetAsync(ctx->res_d.p, 0, sizeof(Counters) + (size_t)2 * ctx->mask_words * sizeof(unsigned), st));
     if (e1) CU(cudaEventRecord(e1, st));
     CU(launch_check(ctx, p));
     if (e2) CU(cudaEventRecord(e2, st));
@@ -1470,7 +1681,16 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
         o.step0 = ctx->scene_step_off[d.scene];
         o.nsteps = ctx->scene_step_off[d.scene + 1] - o.step0;
         o.t0 = d.t0; o.step_limit = d.step_limit;
-        o.cand_base = d.cand_set >= 0 ? ctx->set_off[d.cand_set] + d.cand_off : ctx->set_total + d.cand_off;
+        o.pos_base = -1;
+        o.pad0 = o.pad1 = o.pad2 = 0;
+        if (d.cand_set < 0) {
+            o.cand_base = 2 * ctx->set_total + d.cand_off;
+        } else if (d.cand_off == 0 && d.cand_cnt == ctx->set_off[d.cand_set + 1] - ctx->set_off[d.cand_set] && d.cand_cnt > 512) {
+            o.cand_base = ctx->set_total + ctx->set_off[d.cand_set];        // whole set: spatially sorted copy
+            o.pos_base = ctx->set_off[d.cand_set];
+        } else {
+            o.cand_base = ctx->set_off[d.cand_set] + d.cand_off;
+        }
         o.cand_cnt = d.cand_cnt;
         o.mask_off = (int)words;
         int groups = (d.cand_cnt + 31) / 32;
@@ -1494,13 +1714,13 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
     ctx->up_cand_bytes = bytes_i;
     ctx->up_cand_src = bytes_q + bytes_c + bytes_h;
     // candidate arena = staged sets followed by this call's explicit lists
-    size_t arena = sizeof(int) * (size_t)std::max(ctx->set_total + ncand, 1);
+    size_t arena = sizeof(int) * (size_t)std::max(2 * ctx->set_total + ncand, 1);
     void *arena_before = ctx->cand_d.p;
     CU(ensure(ctx, ctx->cand_d, arena));
     if ((ctx->cand_d.p != arena_before || !ctx->arena_valid) && ctx->set_total)
-        CU(cudaMemcpyAsync(ctx->cand_d.p, ctx->sets.p, sizeof(int) * (size_t)ctx->set_total, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->cand_d.p, ctx->sets.p, sizeof(int) * (size_t)2 * ctx->set_total, cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->arena_valid = true;
-    CU(ensure(ctx, ctx->res_d, sizeof(Counters) + sizeof(unsigned) * (size_t)std::max<long long>(words, 1)));
+    CU(ensure(ctx, ctx->res_d, sizeof(Counters) + sizeof(unsigned) * (size_t)2 * std::max<long long>(words, 1)));
     CU(ensure_result_host(ctx, sizeof(Counters) + sizeof(unsigned) * (size_t)std::max<long long>(words, 1)));
     ctx->B = B; ctx->ctas = (int)ctas; ctx->mask_words = (int)words; ctx->mode = mode;
     ctx->prepared = true;
@@ -1512,7 +1732,7 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
 static int issue_uploads(mpc_ctx *ctx) {
     CU(cudaMemcpyAsync(ctx->qpack_d.p, ctx->h_pin, ctx->up_bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->up_cand_bytes)
-        CU(cudaMemcpyAsync((int *)ctx->cand_d.p + ctx->set_total, (const char *)ctx->h_pin + ctx->up_cand_src, ctx->up_cand_bytes,
+        CU(cudaMemcpyAsync((int *)ctx->cand_d.p + 2 * ctx->set_total, (const char *)ctx->h_pin + ctx->up_cand_src, ctx->up_cand_bytes,
                            cudaMemcpyHostToDevice, ctx->stream));
     return MPC_OK;
 }
@@ -1532,6 +1752,7 @@ static void fill_stats(mpc_ctx *ctx, mpc_stats *st, float ms, int kernels, int o
     st->parity_refined = (int64_t)c.parity_refined;
     st->cull_tests = (int64_t)c.cull_tests;
     st->axis_tests = (int64_t)c.axis_tests;
+    st->box_skipped = (int64_t)c.box_skipped;
     st->worklist_overflow = overflow;
     st->ms_device = ms;
     st->ctas = ctx->ctas;
