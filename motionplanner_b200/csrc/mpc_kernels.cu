@@ -66,7 +66,9 @@ struct Counters {
 
 struct KParams {
     // library
-    const float4 *lib_v, *lib_n, *lib_c;
+    const float4 *lib_v, *lib_n, *lib_c;       // [field][P*J]: gathered through the candidate index
+    const float4 *slib_v, *slib_n, *slib_c;    // [field][J][set_total]: copy in sorted-set order, read coalesced
+    int set_total;
     const double *lib_v64;
     const int *lib_nv, *slot_t;
     int PJ, J, lib_vmax;
@@ -571,24 +573,25 @@ __global__ void __launch_bounds__(K_THREADS, 4) k_check(const KParams p) {
         int nxt_prim = 0;
         {
             const int ci0 = (gbeg + warp) * 32 + lane;
-            if (warp < ng && ci0 < cand_cnt) {
-                nxt_prim = __ldg(p.cand + cand_base + ci0);
-            }
+            if (pos_base < 0 && warp < ng && ci0 < cand_cnt) nxt_prim = __ldg(p.cand + cand_base + ci0);
         }
         for (int g = warp; g < ng; g += NW) {
             // ---- lane = one candidate primitive: transform its occupancy polygon, park it in shared memory ----------
             const int ci = (gbeg + g) * 32 + lane;
             bool active = ci < cand_cnt;
-            int pj = 0;
-            if (active) pj = nxt_prim * p.J + j;
-            {
+            // library record of the lane's candidate: sorted sets have their own copy of the library in set order
+            // (consecutive lanes read consecutive 16-byte records); other candidates are gathered through their index
+            const bool direct = pos_base >= 0;
+            const float4 *Lv = direct ? p.slib_v : p.lib_v, *Ln = direct ? p.slib_n : p.lib_n;
+            const size_t fstride = direct ? (size_t)p.J * p.set_total : (size_t)p.PJ;
+            size_t pj = 0;
+            if (active) pj = direct ? (size_t)j * p.set_total + pos_base + ci : (size_t)nxt_prim * p.J + j;
+            if (!direct) {
                 const int cin = ci + NW * 32;
-                if (g + NW < ng && cin < cand_cnt) {
-                    nxt_prim = __ldg(p.cand + cand_base + cin);
-                }
+                if (g + NW < ng && cin < cand_cnt) nxt_prim = __ldg(p.cand + cand_base + cin);
             }
             float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active) cc = __ldg(p.lib_c + pj);
+            if (active) cc = __ldg((direct ? p.slib_c : p.lib_c) + pj);
             const int nv = (int)cc.w;
             active = active && nv > 0;
             {
@@ -598,7 +601,7 @@ __global__ void __launch_bounds__(K_THREADS, 4) k_check(const KParams p) {
 #pragma unroll
                 for (int h = 0; h < VA / 2; h++) {
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f), n = v;
-                    if (active) { v = __ldg(p.lib_v + (size_t)h * p.PJ + pj); n = __ldg(p.lib_n + (size_t)h * p.PJ + pj); }
+                    if (active) { v = __ldg(Lv + h * fstride + pj); n = __ldg(Ln + h * fstride + pj); }
                     ax[2 * h] = fmaf(lc, v.x, fmaf(-ls, v.y, lx));
                     ay[2 * h] = fmaf(ls, v.x, fmaf(lc, v.y, ly));
                     ax[2 * h + 1] = fmaf(lc, v.z, fmaf(-ls, v.w, lx));
@@ -1062,7 +1065,7 @@ struct mpc_ctx {
     int P = 0, J = 0, lib_vmax = 0, VA = 4;
     double lib_radius = 0.0;
     float lib_rmax = 0.f;
-    DevBuf lib_v, lib_n, lib_c, lib_v64, lib_nv, slot_t, sets;
+    DevBuf lib_v, lib_n, lib_c, lib_v64, lib_nv, slot_t, sets, slib_v, slib_n, slib_c;
     std::vector<int> set_off;
     int nsets = 0, set_total = 0;
     bool arena_valid = false;
@@ -1184,6 +1187,7 @@ extern "C" void mpc_destroy(mpc_ctx *ctx) {
         cudaStreamSynchronize(ctx->stream);
     }
     DevBuf *bufs[] = {&ctx->lib_v, &ctx->lib_n, &ctx->lib_c, &ctx->lib_v64, &ctx->lib_nv, &ctx->slot_t, &ctx->sets,
+                      &ctx->slib_v, &ctx->slib_n, &ctx->slib_c,
                       &ctx->ob_src, &ctx->ob_src_nv, &ctx->ob_src_off, &ctx->ob_c, &ctx->ob_box, &ctx->ob_order, &ctx->step_obst_cnt,
                       &ctx->sets_pos,
                       &ctx->ob_in, &ctx->ob_f, &ctx->ob_nv, &ctx->step_obst_off, &ctx->step_seg_begin,
@@ -1376,9 +1380,28 @@ extern "C" int mpc_upload_library(mpc_ctx *ctx, const double *verts, const int32
                 pos[b + i] = order[i].second;
             }
         }
+        // the library once more, in sorted-set order and slot-major, for coalesced reads by k_check
+        const int H = VA / 2;
+        std::vector<float4> sv((size_t)H * J * std::max(total, 1)), sn(sv.size()), scv((size_t)J * std::max(total, 1));
+        for (int a = 0; a < total; a++) {
+            const size_t pr = (size_t)both[(size_t)total + a];
+            for (int j = 0; j < J; j++) {
+                scv[(size_t)j * total + a] = hc[pr * J + j];
+                for (int h = 0; h < H; h++) {
+                    sv[((size_t)h * J + j) * total + a] = hv[(size_t)h * PJ + pr * J + j];
+                    sn[((size_t)h * J + j) * total + a] = hn[(size_t)h * PJ + pr * J + j];
+                }
+            }
+        }
+        CU(ensure(ctx, ctx->slib_v, sv.size() * sizeof(float4)));
+        CU(ensure(ctx, ctx->slib_n, sn.size() * sizeof(float4)));
+        CU(ensure(ctx, ctx->slib_c, scv.size() * sizeof(float4)));
         CU(ensure(ctx, ctx->sets, both.size() * sizeof(int)));
         CU(ensure(ctx, ctx->sets_pos, pos.size() * sizeof(int)));
         if (total) {
+            CU(cudaMemcpyAsync(ctx->slib_v.p, sv.data(), sv.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->slib_n.p, sn.data(), sn.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->slib_c.p, scv.data(), scv.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
             CU(cudaMemcpyAsync(ctx->sets.p, both.data(), (size_t)2 * total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
             CU(cudaMemcpyAsync(ctx->sets_pos.p, pos.data(), (size_t)total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
@@ -1559,6 +1582,8 @@ static KParams make_params(mpc_ctx *ctx) {
     KParams p;
     memset(&p, 0, sizeof p);
     p.lib_v = (const float4 *)ctx->lib_v.p; p.lib_n = (const float4 *)ctx->lib_n.p; p.lib_c = (const float4 *)ctx->lib_c.p;
+    p.slib_v = (const float4 *)ctx->slib_v.p; p.slib_n = (const float4 *)ctx->slib_n.p; p.slib_c = (const float4 *)ctx->slib_c.p;
+    p.set_total = ctx->set_total;
     p.lib_v64 = (const double *)ctx->lib_v64.p; p.lib_nv = (const int *)ctx->lib_nv.p; p.slot_t = (const int *)ctx->slot_t.p;
     p.PJ = ctx->P * ctx->J; p.J = ctx->J; p.lib_vmax = ctx->lib_vmax;
     p.ob_f = (const float4 *)ctx->ob_f.p; p.ob_c = (const float *)ctx->ob_c.p; p.ob_box = (const float4 *)ctx->ob_box.p;
