@@ -1080,6 +1080,10 @@ struct mpc_ctx {
         sg_box, seg_scene, maxabs;
     int sg_stride = 32;
     float maxabs_scene = 0.f;
+    DevBuf meta;                  // one allocation behind the small per-scene arrays (views below), one H2D copy
+    void *h_meta = nullptr;
+    size_t h_meta_cap = 0;
+    long long meta_sig = 0;
     // queries
     DevBuf qpack_d, cand_d, res_d, wl, flush;
     size_t qpack_cta_off = 0, qpack_hdr_off = 0, up_bytes = 0, up_cand_bytes = 0, up_cand_src = 0;
@@ -1188,17 +1192,17 @@ extern "C" void mpc_destroy(mpc_ctx *ctx) {
     }
     DevBuf *bufs[] = {&ctx->lib_v, &ctx->lib_n, &ctx->lib_c, &ctx->lib_v64, &ctx->lib_nv, &ctx->slot_t, &ctx->sets,
                       &ctx->slib_v, &ctx->slib_n, &ctx->slib_c,
-                      &ctx->ob_src, &ctx->ob_src_nv, &ctx->ob_src_off, &ctx->ob_c, &ctx->ob_box, &ctx->ob_order, &ctx->step_obst_cnt,
+                      &ctx->ob_src, &ctx->ob_src_nv, &ctx->ob_c, &ctx->ob_box, &ctx->ob_order,
                       &ctx->sets_pos,
-                      &ctx->ob_in, &ctx->ob_f, &ctx->ob_nv, &ctx->step_obst_off, &ctx->step_seg_begin,
-                      &ctx->step_seg_end, &ctx->scene_step_off_d, &ctx->origins_d, &ctx->sg_64, &ctx->sg_f,
-                      &ctx->sg_box, &ctx->seg_scene, &ctx->maxabs, &ctx->qpack_d, &ctx->cand_d, &ctx->res_d, &ctx->wl,
+                      &ctx->ob_in, &ctx->ob_f, &ctx->ob_nv, &ctx->meta, &ctx->sg_f,
+                      &ctx->sg_box, &ctx->maxabs, &ctx->qpack_d, &ctx->cand_d, &ctx->res_d, &ctx->wl,
                       &ctx->flush};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
+    if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1495,34 +1499,52 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     }
     const int noslots = slot_off[nsteps];
     const int ob_stride = std::max(noslots, 32), sg_stride = std::max(nslots, 32);
-    CU(ensure(ctx, ctx->scene_step_off_d, (size_t)(nscenes + 1) * sizeof(int)));
-    CU(ensure(ctx, ctx->origins_d, (size_t)nscenes * 2 * sizeof(double)));
-    CU(ensure(ctx, ctx->step_obst_off, (size_t)(nsteps + 1) * sizeof(int)));
-    CU(ensure(ctx, ctx->step_seg_begin, (size_t)std::max(nsteps, 1) * sizeof(int)));
-    CU(ensure(ctx, ctx->step_seg_end, (size_t)std::max(nsteps, 1) * sizeof(int)));
     CU(ensure(ctx, ctx->ob_src, (size_t)std::max(nobst, 1) * VB * 2 * sizeof(double)));
     CU(ensure(ctx, ctx->ob_src_nv, (size_t)std::max(nobst, 1) * sizeof(int)));
-    CU(ensure(ctx, ctx->ob_src_off, (size_t)(nsteps + 1) * sizeof(int)));
-    CU(ensure(ctx, ctx->step_obst_cnt, (size_t)std::max(nsteps, 1) * sizeof(int)));
     CU(ensure(ctx, ctx->ob_in, (size_t)ob_stride * VB * 2 * sizeof(double)));
     CU(ensure(ctx, ctx->ob_nv, (size_t)ob_stride * sizeof(int)));
     CU(ensure(ctx, ctx->ob_f, (size_t)ob_stride * F * sizeof(float4)));
     CU(ensure(ctx, ctx->ob_c, (size_t)ob_stride * 3 * sizeof(float)));
     CU(ensure(ctx, ctx->ob_box, (size_t)(ob_stride / 32 + 1) * sizeof(float4)));
     CU(ensure(ctx, ctx->ob_order, (size_t)ob_stride * sizeof(int)));
-    CU(ensure(ctx, ctx->sg_64, (size_t)sg_stride * 4 * sizeof(double)));
     CU(ensure(ctx, ctx->sg_f, (size_t)sg_stride * 2 * sizeof(float4)));
     CU(ensure(ctx, ctx->sg_box, (size_t)(sg_stride / 32 + 1) * sizeof(float4)));
-    CU(ensure(ctx, ctx->seg_scene, (size_t)sg_stride * sizeof(int)));
     cudaStream_t st = ctx->stream;
-    CU(cudaMemcpyAsync(ctx->scene_step_off_d.p, scene_step_off, (size_t)(nscenes + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->origins_d.p, origins, (size_t)nscenes * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->step_obst_off.p, slot_off.data(), (size_t)(nsteps + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->ob_src_off.p, step_obst_off, (size_t)(nsteps + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-    if (nsteps) CU(cudaMemcpyAsync(ctx->step_obst_cnt.p, step_cnt.data(), (size_t)nsteps * sizeof(int), cudaMemcpyHostToDevice, st));
-    if (nsteps) {
-        CU(cudaMemcpyAsync(ctx->step_seg_begin.p, dev_begin.data(), (size_t)nsteps * sizeof(int), cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(ctx->step_seg_end.p, dev_end.data(), (size_t)nsteps * sizeof(int), cudaMemcpyHostToDevice, st));
+    // the small per-scene arrays travel as one packed block (one driver call instead of nine)
+    {
+        const size_t n_org = (size_t)nscenes * 2 * sizeof(double), n_sg = (size_t)sg_stride * 4 * sizeof(double);
+        const size_t n_sso = (size_t)(nscenes + 1) * 4, n_st1 = (size_t)(nsteps + 1) * 4, n_st = (size_t)std::max(nsteps, 1) * 4;
+        const size_t n_ss = (size_t)sg_stride * 4;
+        size_t off = 0;
+        auto take = [&](size_t n) { size_t o = off; off += (n + 15) / 16 * 16; return o; };
+        const size_t o_org = take(n_org), o_sg = take(n_sg), o_sso = take(n_sso), o_slot = take(n_st1), o_src = take(n_st1),
+                     o_cnt = take(n_st), o_sb = take(n_st), o_se = take(n_st), o_ss = take(n_ss);
+        if (off > ctx->h_meta_cap) {
+            if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
+            ctx->h_meta = nullptr;
+            ctx->h_meta_cap = 0;
+            CU(cudaMallocHost(&ctx->h_meta, off * 2));
+            ctx->h_meta_cap = off * 2;
+        }
+        CU(ensure(ctx, ctx->meta, off));
+        char *h = (char *)ctx->h_meta, *d = (char *)ctx->meta.p;
+        memcpy(h + o_org, origins, n_org);
+        if (nslots) memcpy(h + o_sg, dsegs.data(), (size_t)nslots * 4 * sizeof(double));
+        memcpy(h + o_sso, scene_step_off, n_sso);
+        memcpy(h + o_slot, slot_off.data(), n_st1);
+        memcpy(h + o_src, step_obst_off, n_st1);
+        if (nsteps) {
+            memcpy(h + o_cnt, step_cnt.data(), (size_t)nsteps * 4);
+            memcpy(h + o_sb, dev_begin.data(), (size_t)nsteps * 4);
+            memcpy(h + o_se, dev_end.data(), (size_t)nsteps * 4);
+        }
+        if (nslots) memcpy(h + o_ss, dscene.data(), (size_t)nslots * 4);
+        CU(cudaMemcpyAsync(d, h, off, cudaMemcpyHostToDevice, st));
+        ctx->origins_d.p = d + o_org; ctx->sg_64.p = d + o_sg; ctx->scene_step_off_d.p = d + o_sso;
+        ctx->step_obst_off.p = d + o_slot; ctx->ob_src_off.p = d + o_src; ctx->step_obst_cnt.p = d + o_cnt;
+        ctx->step_seg_begin.p = d + o_sb; ctx->step_seg_end.p = d + o_se; ctx->seg_scene.p = d + o_ss;
+        // captured graphs hold these addresses: a different layout is a different graph
+        ctx->meta_sig = (long long)(o_sg * 1315423911ull ^ o_sso * 2654435761ull ^ o_slot * 40503ull ^ o_ss * 97ull ^ off);
     }
     CU(cudaMemsetAsync(ctx->maxabs.p, 0, sizeof(float), st));
     if (nobst) {
@@ -1554,8 +1576,6 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
         CU(cudaGetLastError());
     }
     if (nslots) {
-        CU(cudaMemcpyAsync(ctx->sg_64.p, dsegs.data(), (size_t)nslots * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(ctx->seg_scene.p, dscene.data(), (size_t)nslots * sizeof(int), cudaMemcpyHostToDevice, st));
         k_stage_segs<<<(nslots + 127) / 128, 128, 0, st>>>(nslots, (const double *)ctx->sg_64.p, (const int *)ctx->seg_scene.p, (const double *)ctx->origins_d.p,
                                                          (float4 *)ctx->sg_f.p, sg_stride, (float4 *)ctx->sg_box.p, (float *)ctx->maxabs.p);
         CU(cudaGetLastError());
@@ -1831,7 +1851,7 @@ static int run_graph(mpc_ctx *ctx, float *ms, bool timed) {
                                   (long long)ctx->up_bytes, (long long)ctx->up_cand_bytes, (long long)ctx->wl_cap,
                                   (long long)ctx->VA, (long long)ctx->VB, (long long)ctx->ob_stride, (long long)ctx->sg_stride,
                                   (long long)ctx->ob_vmax, (long long)ctx->P, (long long)ctx->J, (long long)ctx->lib_vmax,
-                                  (long long)__builtin_bit_cast(unsigned, ctx->lib_rmax), (long long)ctx->set_total};
+                                  (long long)__builtin_bit_cast(unsigned, ctx->lib_rmax), (long long)ctx->set_total, ctx->meta_sig};
     auto it = ctx->graphs.find(key);
     if (it == ctx->graphs.end()) {
         if (ctx->graphs.size() > 256) invalidate_graphs(ctx);
