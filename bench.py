@@ -40,7 +40,7 @@ FLOP_PER_CHECK = 304            # rectangle x rectangle SAT, a =
 SAT_FLOP_EXECUTED = 160         # this kernel's full 4x4 test: 64 FMA (2 flop) + 24 min + 8 max
 CULL_FLOP_EXECUTED = 6          # centre-line axis per pair: 2 add + 2 fma (packed FADD2/FFMA2: two pairs per instruction)
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # no FP32 entry in MEASURED_PEAKS.json: derived from its sm_max_mhz
-NCU_DRAM_BYTES_PER_LAUNCH = 17637632   # ncu capture b (profiles/): dram__bytes_read.sum of one 16-query launch; write 0
+NCU_DRAM_BYTES_PER_LAUNCH = 17630208   # ncu capture f (profiles/): dram__bytes_read.sum of one 16-query launch; write 0
 METRIC = "primitive x obstacle x timestep collision checks/sec"
 
 
@@ -321,19 +321,20 @@ def main():
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH if nq == 16 else None,
                 "what": "executed FP32 flop of the timed launch (an instrumented launch of the same batch counts "
                         "centre-line axis tests x 6 flop and full separating-axis tests x 160 flop) / CUDA-event "
-                        "duration of k_check. The kernel is NOT FP32-bound: ncu (profiles/r01b_k_check_ncu_full.csv) "
-                        "shows the shared-memory data pipe at 78 % and instruction issue at 72 % of peak, FMA pipe "
-                        "28 %; HBM traffic equals the algorithmic bytes.",
+                        "duration of k_check. The kernel is NOT FP32-bound: ncu (profiles/r01f_k_check_ncu_full.csv) "
+                        "shows instruction issue at 79 % and the shared-memory data pipe at 63 % of peak, FMA pipe "
+                        "27 %; block bounding boxes separate 60 % of the pairs wholesale; HBM traffic equals the "
+                        "algorithmic bytes.",
                 "peak_source": "derived: 148 SM x 128 lanes x 2 x sm_max_mhz 1965 (MEASURED_PEAKS.json has no FP32 "
                                "figure)",
                 "kernel_ms": main_ms,
                 "executed": {"cull_axis_tests": st_cnt["cull_tests"], "full_sat_tests": st_cnt["axis_tests"],
-                             "flop": exec_flop},
+                             "pairs_separated_by_block_box": st_cnt["box_skipped"], "flop": exec_flop},
                 "algorithmic_survey": {"flop_per_check": FLOP_PER_CHECK, "achieved": algo_tflops,
                                        "frac": algo_tflops / FP32_PEAK_TFLOPS,
                                        "note": "SURVEY.md 8(d) definition: 304 flop x checks / time. Above 1 by "
-                                               "construction: the centre-line axis decides 99.6 % of the pairs with "
-                                               "6 flop, so the algorithmic count is not executed."},
+                                               "construction: block boxes and the centre-line axis (6 flop) decide "
+                                               "99.6 % of the pairs, so the algorithmic count is not executed."},
                 "full_evaluation": {"checks_per_s": full_checks / (full_main * 1e-3),
                                     "achieved": full_checks * SAT_FLOP_EXECUTED / (full_main * 1e-3) / 1e12,
                                     "frac": full_checks * SAT_FLOP_EXECUTED / (full_main * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
@@ -341,8 +342,8 @@ def main():
                                     "note": "MPC_MODE_NO_CULL|NO_EARLY_EXIT: every pair runs the complete 4x4 "
                                             "separating-axis test (160 executed flop: 64 FMA + 32 min/max); here "
                                             "algorithmic = executed"},
-                "ncu": {"source": "profiles/r01b_k_check_ncu_full.csv", "smsp__issue_active_pct": 72.3,
-                        "l1tex__data_pipe_lsu_wavefronts_pct": 78.1, "sm__inst_executed_pipe_fma_pct": 28.3,
+                "ncu": {"source": "profiles/r01f_k_check_ncu_full.csv", "smsp__issue_active_pct": 78.7,
+                        "l1tex__data_pipe_lsu_wavefronts_pct": 63.0, "sm__inst_executed_pipe_fma_pct": 26.9,
                         "dram__bytes_read": NCU_DRAM_BYTES_PER_LAUNCH, "dram__bytes_write": 0},
                 "hbm": {"algorithmic_bytes": algo_bytes, "achieved_gbs": algo_bytes / (main_ms * 1e-3) / 1e9,
                         "peak_gbs": hbm_peak, "frac": algo_bytes / (main_ms * 1e-3) / 1e9 / hbm_peak,
