@@ -30,8 +30,14 @@ def collision_flags(scenario, traj, param, engine=None):
     n = traj.shape[1]
     road = _road_of(scenario)
     off, obst, nv = scenario_obstacle_arrays(scenario, n)
-    lib = car_library(param['length'], param['width'])
-    engine.upload_library(lib['verts'], lib['nv'], lib['tidx'])
+    key = ('car', float(param['length']), float(param['width']))
+    if getattr(engine, '_staged_library', None) != key:
+        lib = car_library(param['length'], param['width'])
+        engine.upload_library(lib['verts'], lib['nv'], lib['tidx'])
+        try:
+            engine._staged_library = key
+        except AttributeError:
+            pass
     scenes = SceneSet()
     scenes.add_scene_explicit(n, off, obst, nv, road.segments, origin=traj[0:2, 0])
     scenes.stage(engine)

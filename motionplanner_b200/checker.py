@@ -214,7 +214,15 @@ class PrimitiveChecker:
         self.layout = MA.device_layout(time_step)
         self.backend = backend if backend is not None else get_engine('planner')
         lay = self.layout
-        self.backend.upload_library(lay['verts'], lay['nv'], lay['tidx'], lay['set_off'], lay['set_idx'])
+        # the library is staged once per (engine, automaton, time step): replanning only re-stages the scene
+        key = (id(MA), float(time_step), len(MA.primitives))
+        if getattr(self.backend, '_staged_library', None) != key:
+            self.backend.upload_library(lay['verts'], lay['nv'], lay['tidx'], lay['set_off'], lay['set_idx'])
+            try:
+                self.backend._staged_library = key
+                self.backend._staged_library_ref = MA          # keeps id(MA) from being reused
+            except AttributeError:
+                pass
         self.index_of = {id(p): i for i, p in enumerate(MA.primitives)}
         self._set_len = np.diff(lay['set_off'])
         self._qbuf = {}

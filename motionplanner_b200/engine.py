@@ -110,6 +110,7 @@ class CollisionEngine:
             set_off = _arr(set_off, np.int32)
             set_idx = _arr(set_idx, np.int32)
             nsets = len(set_off) - 1
+        self._staged_library = None          # whoever staged through a cache key sets it again after this call
         self._check(self._L.mpc_upload_library(self._ctx, _cabi.ptr(verts), _cabi.ptr(nv), _cabi.ptr(tidx), P, J, V,
                                                _cabi.ptr(set_off) if nsets else None,
                                                _cabi.ptr(set_idx) if nsets else None, nsets), "mpc_upload_library")
