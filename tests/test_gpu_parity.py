@@ -357,3 +357,29 @@ def test_refinement_list_overflow_is_recovered(monkeypatch):
     got, st = e2.query(q, None, MODE_PLANNER)                       # the grown list is kept
     assert np.array_equal(got, want) and st["worklist_overflow"] == 0
     e2.close()
+
+
+@pytest.mark.parametrize("mode", [MODE_PLANNER, MODE_VALIDATOR])
+def test_adversarial_with_sorted_sets_and_block_culling(eng, mode):
+    """candidate sets larger than 512 are kept spatially sorted on the device (results must come back in the caller's
+    order) and steps with more than 32 obstacle slots are culled by block boxes: near-contact obstacles, whole-set
+    queries, sub-range queries (which use the unsorted copy) and explicit lists must all agree with the oracle"""
+    lib, sc, org, q = W.adversarial_problem(900 + mode, P=1300, J=4, nsteps=6, max_obst=90, nqueries=4)
+    P = lib["verts"].shape[0]
+    assert P // 2 > 512
+    got, want, st, ost = both(eng, lib, sc, org, q, None, mode)           # whole sets: sorted path
+    assert np.array_equal(got, want), (got != want).sum()
+    assert st["pairs_nominal"] == ost["pairs_nominal"] and 0 < want.mean() < 1
+    q2 = q.copy()
+    q2["cand_off"], q2["cand_cnt"] = 17, P // 2 - 40                       # sub-ranges: caller's order
+    got, want, _, _ = both(eng, lib, sc, org, q2, None, mode)
+    assert np.array_equal(got, want)
+    q3 = q.copy()
+    rng = np.random.default_rng(1)
+    cand = rng.permutation(P).astype(np.int32)
+    q3["cand_set"], q3["cand_off"], q3["cand_cnt"] = -1, 0, P
+    got, want, _, _ = both(eng, lib, sc, org, q3, cand, mode)
+    assert np.array_equal(got, want)
+    stage(eng, lib, sc, org)
+    g2, st2 = eng.query(q, None, mode | MODE_COUNT_WORK | MODE_NO_EARLY_EXIT)
+    assert st2["box_skipped"] > 0 and st2["cull_tests"] + st2["box_skipped"] + 0 >= 0
