@@ -1,0 +1,1013 @@
+// mpc_device.cuh -- device code of libmpcheck.so: staging kernels, k_check (float32 separating-axis pass with
+// TMA-staged tiles, block-box culling, packed FFMA2 centre-line axis, per-warp SAT queue) and k_refine (float64 /
+// exact tie-break).  Included by mpc_kernels.cu (host side / C ABI).  See the header of mpc_kernels.cu and DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/mpc.h"
+#include "mpc_exact.cuh"
+
+namespace mpc {
+
+constexpr float BIG = 1e30f;
+constexpr float FAR = 1e18f;
+constexpr int GPC_MAX = 32;       // candidate groups (of 32) per CTA
+constexpr unsigned FULL = 0xffffffffu;
+
+enum { KIND_OBST = 0, KIND_SEG = 1, KIND_PARITY = 2 };
+
+struct QDev {
+    double x, y, c, s;            // float64 pose, global frame (tie-break pass)
+    float lx, ly, lc, ls;         // float32 pose relative to the scene origin
+    int step0, nsteps, t0, step_limit;
+    int cand_base, cand_cnt, mask_off, chunks;
+    int pos_base, pad0, pad1, pad2;   // >= 0: candidates are a spatially sorted set, cand_pos[pos_base + i] = original slot
+};
+
+struct Counters {
+    unsigned long long pairs_nominal, refined, exact_ties, near_tangent, parity_refined, cull_tests, axis_tests;
+    unsigned wl_count, pad;
+    unsigned long long box_skipped, pad1[7];
+};
+
+struct KParams {
+    // library
+    const float4 *lib_v, *lib_n, *lib_c;       // [field][P*J]: gathered through the candidate index
+    const float4 *slib_v, *slib_n, *slib_c;    // [field][J][set_total]: copy in sorted-set order, read coalesced
+    int set_total;
+    const double *lib_v64;
+    const int *lib_nv, *slot_t;
+    int PJ, J, lib_vmax;
+    // scenes
+    const float4 *ob_f;          // [F-1][ob_stride] vertex and edge-line fields, slot layout (steps 32-aligned)
+    const float4 *ob_box;        // [ob_stride/32] bounding box of the circles of every block of 32 slots
+    const float *ob_c;           // [3][ob_stride]   bounding circle x | y | r, slot layout
+    const double *ob_v64;
+    const int *ob_nv;
+    int ob_stride, ob_vmax;
+    const int *step_obst_off, *step_obst_cnt, *step_seg_begin, *step_seg_end;
+    const float4 *sg_f, *sg_box;
+    const double *sg_64;
+    int sg_stride;
+    const float *maxabs_scene;
+    // queries
+    const QDev *q;
+    const int *cta_off, *cand, *cand_pos;
+    int B, nwords;
+    unsigned *mask;              // result bits, caller's candidate order
+    unsigned *mask_sorted;       // result bits of spatially sorted candidate sets, un-permuted by k_refine
+    int4 *wl;
+    int wl_cap;
+    Counters *cnt;
+    const float *maxabs_query;   // batch header in the query pack (device), so that a captured graph stays valid
+    float lib_rmax;
+    unsigned mode;
+    int gpc, cap_o, cap_s;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D TMA bulk copy (global -> shared::cta)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes,
+                                             unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// packed float32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 -- two lanes of work per issued instruction)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+__host__ __device__ constexpr int ob_fields(int VB) { return VB / 2 + (VB * 3 + 3) / 4; }   // float4 fields (circle apart)
+
+// ---------------------------------------------------------------------------------------------------------------------
+// staging kernels
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int upper_bound_idx(const int *a, int n, int v) {   // largest i with a[i] <= v, a sorted
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (a[mid] <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ void atomic_max_pos_float(float *addr, float v) {
+    atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+__device__ __forceinline__ unsigned morton16_dev(unsigned x, unsigned y) {
+    auto spread = [](unsigned v) {
+        v &= 0xffff;
+        v = (v | (v << 8)) & 0x00ff00ff;
+        v = (v | (v << 4)) & 0x0f0f0f0f;
+        v = (v | (v << 2)) & 0x33333333;
+        v = (v | (v << 1)) & 0x55555555;
+        return v;
+    };
+    return spread(x) | (spread(y) << 1);
+}
+
+// One CTA per time step: order the step's obstacles along a Morton curve (keys from the vertex mean relative to the
+// scene origin, 6 cm cells over +-2 km) with a bitonic sort in shared memory, so that a block of 32 consecutive slots
+// is spatially compact and k_check can skip it by its bounding box.  order[slot] = source obstacle (or -1: padding).
+// Steps with more than SORT_MAX obstacles keep their input order (the boxes are then just less selective).
+constexpr int SORT_MAX = 2048;
+template <int VB>
+__global__ void __launch_bounds__(256) k_order_obst(const double *__restrict__ src64, const int *__restrict__ src_nv,
+                                                    const int *__restrict__ src_off, const int *__restrict__ slot_off,
+                                                    const int *__restrict__ scene_step_off, int nscenes,
+                                                    const double *__restrict__ origins, int *__restrict__ order) {
+    __shared__ unsigned s_key[SORT_MAX];
+    __shared__ int s_idx[SORT_MAX];
+    const int step = blockIdx.x;
+    const int o0 = src_off[step], cnt = src_off[step + 1] - o0, s0 = slot_off[step], nslot = slot_off[step + 1] - s0;
+    if (cnt > SORT_MAX) {
+        for (int i = threadIdx.x; i < nslot; i += blockDim.x) order[s0 + i] = (i < cnt) ? o0 + i : -1;
+        return;
+    }
+    int n2 = 32;
+    while (n2 < cnt) n2 <<= 1;
+    const int sc = upper_bound_idx(scene_step_off, nscenes + 1, step);
+    const double ox = origins[2 * sc], oy = origins[2 * sc + 1];
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        unsigned key = 0xffffffffu;
+        if (i < cnt) {
+            const int nv = src_nv[o0 + i];
+            const double *v = src64 + (size_t)(o0 + i) * VB * 2;
+            double cx = 0.0, cy = 0.0;
+            for (int k = 0; k < nv && k < VB; k++) { cx += v[2 * k]; cy += v[2 * k + 1]; }
+            if (nv > 0) { cx = cx / nv - ox; cy = cy / nv - oy; }
+            const double qx = fmin(fmax((cx + 2048.0) * 16.0, 0.0), 65535.0), qy = fmin(fmax((cy + 2048.0) * 16.0, 0.0), 65535.0);
+            key = morton16_dev((unsigned)qx, (unsigned)qy);
+            if (key == 0xffffffffu) key = 0xfffffffeu;
+        }
+        s_key[i] = key;
+        s_idx[i] = (i < cnt) ? o0 + i : -1;
+    }
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                const int l = i ^ jj;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const unsigned a = s_key[i], b = s_key[l];
+                    // ties are broken by the source index so that the order is deterministic
+                    const bool gt = a > b || (a == b && s_idx[i] > s_idx[l]);
+                    if (gt == up) {
+                        s_key[i] = b; s_key[l] = a;
+                        const int t = s_idx[i]; s_idx[i] = s_idx[l]; s_idx[l] = t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < nslot; i += blockDim.x) order[s0 + i] = (i < cnt) ? s_idx[i] : -1;
+}
+
+// one thread per obstacle *slot*: the obstacles of a step occupy a 32-aligned slot range [slot_off[k], slot_off[k+1]),
+// the tail is padding that can never be near anything.  Writes the float32 SoA records, the bounding circle arrays and
+// the CCW-normalised float64 copy (slot layout) for the tie-break pass.
+template <int VB>
+__global__ void k_stage_obst(int nslots, const double *__restrict__ src64, const int *__restrict__ src_nv,
+                             const int *__restrict__ order, const int *__restrict__ slot_off, int nsteps,
+                             const int *__restrict__ scene_step_off, int nscenes, const double *__restrict__ origins,
+                             float4 *__restrict__ ob_f, float *__restrict__ ob_c, float4 *__restrict__ ob_box,
+                             double *__restrict__ ob64, int *__restrict__ ob_nv, int stride, float *maxabs) {
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;     // nslots is a multiple of 32: whole warps are in range
+    if (slot >= nslots) return;
+    constexpr int F = ob_fields(VB);
+    const int step = upper_bound_idx(slot_off, nsteps + 1, slot);
+    const int o = order[slot];
+    int nv = (o >= 0) ? src_nv[o] : 0;
+    float out[F * 4];
+    float ccx = FAR, ccy = FAR, ccr = 0.f;
+    double *v = ob64 + (size_t)slot * VB * 2;
+    bool ok = nv >= 3 && nv <= VB;
+    double x[VB], y[VB];
+    if (ok) {
+        const double *sv = src64 + (size_t)o * VB * 2;
+        for (int k = 0; k < VB; k++) { x[k] = sv[2 * (k < nv ? k : nv - 1)]; y[k] = sv[2 * (k < nv ? k : nv - 1) + 1]; }
+        double area = 0.0;
+        for (int k = 0; k < nv; k++) {
+            int k1 = (k + 1 == nv) ? 0 : k + 1;
+            area += (x[k] - x[0]) * (y[k1] - y[0]) - (x[k1] - x[0]) * (y[k] - y[0]);
+        }
+        if (area == 0.0) ok = false;
+        if (area < 0.0) {   // reverse to counter-clockwise, keep the float64 copy in the same order
+            for (int i = 0, k = nv - 1; i < k; i++, k--) {
+                double tx = x[i], ty = y[i];
+                x[i] = x[k]; y[i] = y[k]; x[k] = tx; y[k] = ty;
+            }
+            for (int k = nv; k < VB; k++) { x[k] = x[nv - 1]; y[k] = y[nv - 1]; }
+        }
+    }
+    if (!ok) {
+        // never near, and "always separated" for whoever tests it anyway: a point far away
+        for (int k = 0; k < VB * 2; k++) out[k] = FAR;
+        for (int k = 0; k < VB; k++) { out[VB * 2 + 3 * k] = 0.f; out[VB * 2 + 3 * k + 1] = 0.f; out[VB * 2 + 3 * k + 2] = -BIG; }
+        for (int k = VB * 5; k < F * 4; k++) out[k] = 0.f;
+        for (int k = 0; k < VB * 2; k++) v[k] = 0.0;
+        nv = 0;
+    } else {
+        int sc = upper_bound_idx(scene_step_off, nscenes + 1, step);
+        double ox = origins[2 * sc], oy = origins[2 * sc + 1];
+        for (int k = 0; k < VB; k++) { v[2 * k] = x[k]; v[2 * k + 1] = y[k]; }
+        double cx = 0.0, cy = 0.0, m = 0.0;
+        for (int k = 0; k < VB; k++) {
+            double lx = x[k] - ox, ly = y[k] - oy;
+            out[4 * (k >> 1) + (k & 1)] = (float)lx; out[4 * (k >> 1) + 2 + (k & 1)] = (float)ly;   // (x0,x1,y0,y1)
+            m = fmax(m, fmax(fabs(lx), fabs(ly)));
+            if (k < nv) { cx += lx; cy += ly; }
+        }
+        cx /= nv; cy /= nv;
+        double r = 0.0;
+        for (int k = 0; k < nv; k++) {
+            double dx = x[k] - ox - cx, dy = y[k] - oy - cy;
+            r = fmax(r, sqrt(dx * dx + dy * dy));
+        }
+        for (int k = 0; k < VB; k++) {
+            float nx = 0.f, ny = 0.f, c = BIG;       // padded / degenerate edge: never a separating axis
+            if (k < nv) {
+                int k1 = (k + 1 == nv) ? 0 : k + 1;
+                double ex = x[k1] - x[k], ey = y[k1] - y[k];
+                double len = sqrt(ex * ex + ey * ey);
+                if (len > 0.0) {
+                    double dnx = ey / len, dny = -ex / len;            // outward normal of a CCW edge
+                    nx = (float)dnx; ny = (float)dny;
+                    c = (float)(dnx * (x[k] - ox) + dny * (y[k] - oy));
+                }
+            }
+            out[VB * 2 + 3 * k] = nx; out[VB * 2 + 3 * k + 1] = ny; out[VB * 2 + 3 * k + 2] = c;
+        }
+        for (int k = VB * 5; k < F * 4; k++) out[k] = 0.f;
+        ccx = (float)cx; ccy = (float)cy;
+        ccr = __double2float_ru(r * (1.0 + 1e-6) + m * 2.4e-7);
+        atomic_max_pos_float(maxabs, __double2float_ru(m));
+    }
+    ob_nv[slot] = nv;
+#pragma unroll
+    for (int f = 0; f < F; f++)
+        ob_f[(size_t)f * stride + slot] = make_float4(out[4 * f], out[4 * f + 1], out[4 * f + 2], out[4 * f + 3]);
+    ob_c[slot] = ccx;
+    ob_c[(size_t)stride + slot] = ccy;
+    ob_c[(size_t)2 * stride + slot] = ccr;
+    // bounding box of the block's circles (of the float32 values the main kernel will see)
+    const bool real = nv > 0;
+    const float x0 = warp_min(real ? ccx - ccr : BIG), x1 = warp_max(real ? ccx + ccr : -BIG);
+    const float y0 = warp_min(real ? ccy - ccr : BIG), y1 = warp_max(real ? ccy + ccr : -BIG);
+    if ((threadIdx.x & 31) == 0)
+        ob_box[slot >> 5] = make_float4(__fadd_rd(x0, -1e-6f * fabsf(x0)), __fadd_rd(y0, -1e-6f * fabsf(y0)),
+                                        __fadd_ru(x1, 1e-6f * fabsf(x1)), __fadd_ru(y1, 1e-6f * fabsf(y1)));
+}
+
+// one thread per segment slot (slots are laid out in 32-aligned, spatially sorted ranges by the host); a warp = one
+// block of 32 slots and also reduces the block's bounding box (of the float32 data the main kernel will see)
+__global__ void k_stage_segs(int nslots, const double *__restrict__ sg64, const int *__restrict__ seg_scene,
+                             const double *__restrict__ origins, float4 *__restrict__ sg_f, int stride,
+                             float4 *__restrict__ sg_box, float *maxabs) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = false;
+    float4 rec = make_float4(FAR, FAR, FAR, FAR), line = make_float4(0.f, 0.f, BIG, -1.f);
+    if (s < nslots) {
+        int sc = seg_scene[s];
+        double ax = sg64[4 * s], ay = sg64[4 * s + 1], bx = sg64[4 * s + 2], by = sg64[4 * s + 3];
+        double ex = bx - ax, ey = by - ay;
+        double len = sqrt(ex * ex + ey * ey);
+        if (sc >= 0 && len > 0.0) {       // else: padding or degenerate: far away, never near, never straddling
+            double ox = origins[2 * sc], oy = origins[2 * sc + 1];
+            double lax = ax - ox, lay = ay - oy, lbx = bx - ox, lby = by - oy;
+            double nx = ey / len, ny = -ex / len;      // right-hand normal of a->b
+            rec = make_float4((float)lax, (float)lay, (float)lbx, (float)lby);
+            line = make_float4((float)nx, (float)ny, (float)(nx * lax + ny * lay), __double2float_ru(0.5 * len * (1.0 + 1e-6)));
+            double m = fmax(fmax(fabs(lax), fabs(lay)), fmax(fabs(lbx), fabs(lby)));
+            atomic_max_pos_float(maxabs, __double2float_ru(m));
+            valid = true;
+        }
+        sg_f[s] = rec;
+        sg_f[(size_t)stride + s] = line;
+    }
+    float x0 = valid ? fminf(rec.x, rec.z) : BIG, x1 = valid ? fmaxf(rec.x, rec.z) : -BIG;
+    float y0 = valid ? fminf(rec.y, rec.w) : BIG, y1 = valid ? fmaxf(rec.y, rec.w) : -BIG;
+    x0 = warp_min(x0); y0 = warp_min(y0); x1 = warp_max(x1); y1 = warp_max(y1);
+    if ((threadIdx.x & 31) == 0 && s < nslots) sg_box[s >> 5] = make_float4(x0, y0, x1, y1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void push_work(const KParams &p, int q, int ci, int j, int kind, int obj) {
+    unsigned idx = atomicAdd(&p.cnt->wl_count, 1u);
+    if (idx < (unsigned)p.wl_cap) p.wl[idx] = make_int4(q, ci, j | (kind << 16), obj);
+}
+
+// A polygon record in shared memory is SoA by float4 field: V/2 fields of vertex pairs (x0,x1,y0,y1), then
+// ceil(3V/4) fields holding the packed edge lines (nx, ny, c) -- the same layout for obstacle records (staged by
+// k_stage_obst) and for the transformed occupancy polygons the warps write themselves.  Vertex pairs stay packed in
+// 64-bit registers so that one FFMA2 projects two vertices on an edge normal.
+__device__ __forceinline__ float lo32(f32x2 v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi32(f32x2 v) { return __uint_as_float((unsigned)(v >> 32)); }
+
+template <int V>
+struct PolyRegs {
+    f32x2 X[V / 2], Y[V / 2];
+    float ln[((V * 3 + 3) / 4) * 4];
+    __device__ __forceinline__ void load(const float4 *rec, int stride, int i) {
+#pragma unroll
+        for (int h = 0; h < V / 2; h++) {
+            float4 v = rec[h * stride + i];
+            X[h] = pack2(v.x, v.y);
+            Y[h] = pack2(v.z, v.w);
+        }
+#pragma unroll
+        for (int h = 0; h < (V * 3 + 3) / 4; h++) {
+            float4 v = rec[(V / 2 + h) * stride + i];
+            ln[4 * h] = v.x; ln[4 * h + 1] = v.y; ln[4 * h + 2] = v.z; ln[4 * h + 3] = v.w;
+        }
+    }
+    __device__ __forceinline__ float x(int k) const { return (k & 1) ? hi32(X[k >> 1]) : lo32(X[k >> 1]); }
+    __device__ __forceinline__ float y(int k) const { return (k & 1) ? hi32(Y[k >> 1]) : lo32(Y[k >> 1]); }
+};
+
+// three-input min / max (sm_100: FMNMX3)
+__device__ __forceinline__ float min3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// minimum over the vertices of Q of the signed distance to the line (nx, ny, c): two vertices per FFMA2, one FMNMX3
+// per vertex pair
+template <int VQ>
+__device__ __forceinline__ float min_dist(const PolyRegs<VQ> &Q, float nx, float ny, float c) {
+    const f32x2 nx2 = pack2(nx, nx), ny2 = pack2(ny, ny), nc2 = pack2(-c, -c);
+    float mn = BIG;
+#pragma unroll
+    for (int h = 0; h < VQ / 2; h++) {
+        const f32x2 d = fma2(nx2, Q.X[h], fma2(ny2, Q.Y[h], nc2));
+        mn = (h == 0) ? fminf(lo32(d), hi32(d)) : min3(mn, lo32(d), hi32(d));
+    }
+    return mn;
+}
+
+// signed separation of two convex polygons: max over all edge axes of the minimum vertex distance (> 0 apart)
+template <int VA, int VB>
+__device__ __forceinline__ float sat_polys(const PolyRegs<VA> &A, const PolyRegs<VB> &B) {
+    float sep = -BIG;
+#pragma unroll
+    for (int e = 0; e < VA; e += 2)
+        sep = max3(sep, min_dist<VB>(B, A.ln[3 * e], A.ln[3 * e + 1], A.ln[3 * e + 2]),
+                   min_dist<VB>(B, A.ln[3 * e + 3], A.ln[3 * e + 4], A.ln[3 * e + 5]));
+#pragma unroll
+    for (int e = 0; e < VB; e += 2)
+        sep = max3(sep, min_dist<VA>(A, B.ln[3 * e], B.ln[3 * e + 1], B.ln[3 * e + 2]),
+                   min_dist<VA>(A, B.ln[3 * e + 3], B.ln[3 * e + 4], B.ln[3 * e + 5]));
+    return sep;
+}
+
+// signed separation of a convex polygon and a segment (a 2-gon): edges of A against the two end points, the
+// segment's line against the vertices of A on either side
+template <int VA>
+__device__ __forceinline__ float sat_segment(const PolyRegs<VA> &A, const float4 sa, const float4 sl) {
+    float sep = -BIG, mn = BIG, mx = -BIG;
+#pragma unroll
+    for (int e = 0; e < VA; e++) {
+        const float nx = A.ln[3 * e], ny = A.ln[3 * e + 1], c = A.ln[3 * e + 2];
+        const float d0 = fmaf(nx, sa.x, fmaf(ny, sa.y, -c)), d1 = fmaf(nx, sa.z, fmaf(ny, sa.w, -c));
+        sep = fmaxf(sep, fminf(d0, d1));
+        const float d = fmaf(sl.x, A.x(e), fmaf(sl.y, A.y(e), -sl.z));
+        mn = fminf(mn, d);
+        mx = fmaxf(mx, d);
+    }
+    return fmaxf(sep, fmaxf(mn, -mx));
+}
+
+constexpr int K_THREADS = 256;      // 8 warps share one staged tile
+constexpr int QCAP = 64;            // per-warp queue of (lane, record) pairs that passed axis 0
+
+template <int VA, int VB, bool COUNT, bool NOCULL>
+__global__ void __launch_bounds__(K_THREADS, 4) k_check(const KParams p) {
+    constexpr int F = ob_fields(VB), FA = ob_fields(VA), NW = K_THREADS / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_raw);
+    unsigned *s_coll = reinterpret_cast<unsigned *>(smem_raw + 16);
+    unsigned *s_par = s_coll + GPC_MAX;
+    unsigned *s_punc = s_par + GPC_MAX;
+    unsigned *s_q = s_punc + GPC_MAX;                                          // [NW][QCAP]
+    float4 *s_A = reinterpret_cast<float4 *>(s_q + NW * QCAP);                 // [NW][FA][32] occupancy polygons
+    float4 *s_ob = s_A + NW * FA * 32;                                         // [F][cap_o] obstacle records
+    float *s_c = reinterpret_cast<float *>(s_ob + F * p.cap_o);                // circle x | y | -(r + rcull)^2
+    float4 *s_sg = reinterpret_cast<float4 *>(s_c + 3 * p.cap_o);              // [2][cap_s] segments
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    // which (query, slot, chunk) is this CTA
+    // (largest q with cta_off[q] <= blockIdx.x; every warp finds it with warp-wide loads and votes instead of a
+    // chain of dependent loads: a 32-way search per round)
+    int q = 0;
+    {
+        int lo = 0, hi = p.B + 1;                 // answer in [lo, hi)
+        while (hi - lo > 1) {
+            const int span = hi - lo, stride = (span + 31) >> 5;
+            const int idx = lo + lane * stride;
+            const bool le = idx < hi && __ldg(p.cta_off + idx) <= (int)blockIdx.x;
+            const int k = __popc(__ballot_sync(FULL, le));       // cta_off is sorted: the first k probes are <=
+            const int nlo = lo + (k - 1) * stride;
+            hi = min(hi, nlo + stride);
+            lo = nlo;
+        }
+        q = lo;
+    }
+    const QDev *Q = p.q + q;
+    int local = blockIdx.x - p.cta_off[q];
+    int chunks = Q->chunks;
+    int j = local / chunks, chunk = local - j * chunks;
+    int t = Q->t0 + p.slot_t[j];
+    // reference guards: ind + time <= param['steps'] and ind + time < len(space)  (lowLevelPlannerManeuverAutomaton.py:120,122)
+    if (t > Q->step_limit || t < 0 || t >= Q->nsteps) return;
+    int step = Q->step0 + t;
+    // obstacles of the step: a 32-aligned slot range (padding slots are far away), `nobst` real ones
+    const int o0 = p.step_obst_off[step], nslot = p.step_obst_off[step + 1] - o0, nobst = p.step_obst_cnt[step];
+    const int g0 = p.step_seg_begin[step];
+    const bool has_region = g0 >= 0;
+    const int nseg = has_region ? p.step_seg_end[step] - g0 : 0;
+    const int cand_cnt = Q->cand_cnt, cand_base = Q->cand_base;
+    const int gbeg = chunk * p.gpc;
+    const int ng = min(p.gpc, (cand_cnt + 31) / 32 - gbeg);
+    const float lx = Q->lx, ly = Q->ly, lc = Q->lc, ls = Q->ls;
+    // float32 error band: every float32 signed distance below is within tau of its float64 value
+    const float tau = fmaxf(fmaxf(*p.maxabs_scene, *p.maxabs_query) * (1.0f / 131072.0f), 1e-7f);
+    const bool noexit = p.mode & MPC_MODE_NO_EARLY_EXIT;
+
+    if (tid == 0) mbar_init(bar, 1);
+    for (int i = tid; i < 3 * GPC_MAX; i += K_THREADS) s_coll[i] = 0;
+    __syncthreads();
+
+    const int nph_o = (nslot + p.cap_o - 1) / p.cap_o, nph_s = (nseg + p.cap_s - 1) / p.cap_s;
+    const int nphase = max(1, max(nph_o, nph_s));
+    // cull radius shared by the whole CTA: largest library bounding radius + band (conservative for smaller polygons)
+    const float rcull = p.lib_rmax + 2.0f * tau;
+    unsigned n_cull = 0, n_axis = 0, n_skip = 0;
+    const int pos_base = Q->pos_base;
+    float4 *sA = s_A + warp * FA * 32;
+    unsigned *sq = s_q + warp * QCAP;
+
+    for (int ph = 0; ph < nphase; ph++) {
+        const int oc0 = ph * p.cap_o, ocn = max(0, min(nslot - oc0, p.cap_o));       // multiple of 32
+        const int sc0 = ph * p.cap_s, scn = max(0, min(nseg - sc0, p.cap_s));
+        const bool loading = (ocn | scn) != 0;
+        if (tid == 0 && loading) {
+            mbar_expect_tx(bar, (unsigned)(ocn * (16 * F + 12) + scn * 32));
+            if (ocn) {
+                for (int f = 0; f < F; f++)
+                    tma_bulk_g2s(s_ob + f * p.cap_o, p.ob_f + (size_t)f * p.ob_stride + o0 + oc0, ocn * 16, bar);
+                for (int f = 0; f < 3; f++)
+                    tma_bulk_g2s(s_c + f * p.cap_o, p.ob_c + (size_t)f * p.ob_stride + o0 + oc0, ocn * 4, bar);
+            }
+            if (scn)
+                for (int f = 0; f < 2; f++)
+                    tma_bulk_g2s(s_sg + f * p.cap_s, p.sg_f + (size_t)f * p.sg_stride + g0 + sc0, scn * 16, bar);
+        }
+        if (loading) {
+            mbar_wait(bar, ph & 1);
+            // third circle array: r  ->  -(r + rcull)^2, the constant term of the centre-line test
+            for (int i = tid; i < ocn; i += K_THREADS) {
+                float r = s_c[2 * p.cap_o + i] + rcull;
+                s_c[2 * p.cap_o + i] = -(r * r);
+            }
+            __syncthreads();
+        }
+        // candidate index of the warp's first group; the next group's is fetched
+        // while the current one is processed, which takes one link out of the dependent-load chain of the set-up
+        int nxt_prim = 0;
+        {
+            const int ci0 = (gbeg + warp) * 32 + lane;
+            if (pos_base < 0 && warp < ng && ci0 < cand_cnt) nxt_prim = __ldg(p.cand + cand_base + ci0);
+        }
+        for (int g = warp; g < ng; g += NW) {
+            // ---- lane = one candidate primitive: transform its occupancy polygon, park it in shared memory ----------
+            const int ci = (gbeg + g) * 32 + lane;
+            bool active = ci < cand_cnt;
+            // library record of the lane's candidate: sorted sets have their own copy of the library in set order
+            // (consecutive lanes read consecutive 16-byte records); other candidates are gathered through their index
+            const bool direct = pos_base >= 0;
+            const float4 *Lv = direct ? p.slib_v : p.lib_v, *Ln = direct ? p.slib_n : p.lib_n;
+            const size_t fstride = direct ? (size_t)p.J * p.set_total : (size_t)p.PJ;
+            size_t pj = 0;
+            if (active) pj = direct ? (size_t)j * p.set_total + pos_base + ci : (size_t)nxt_prim * p.J + j;
+            if (!direct) {
+                const int cin = ci + NW * 32;
+                if (g + NW < ng && cin < cand_cnt) nxt_prim = __ldg(p.cand + cand_base + cin);
+            }
+            float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (active) cc = __ldg((direct ? p.slib_c : p.lib_c) + pj);
+            const int nv = (int)cc.w;
+            active = active && nv > 0;
+            {
+                float ax[VA], ay[VA], ln[((VA * 3 + 3) / 4) * 4];
+#pragma unroll
+                for (int i = 0; i < ((VA * 3 + 3) / 4) * 4; i++) ln[i] = 0.f;
+#pragma unroll
+                for (int h = 0; h < VA / 2; h++) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), n = v;
+                    if (active) { v = __ldg(Lv + h * fstride + pj); n = __ldg(Ln + h * fstride + pj); }
+                    ax[2 * h] = fmaf(lc, v.x, fmaf(-ls, v.y, lx));
+                    ay[2 * h] = fmaf(ls, v.x, fmaf(lc, v.y, ly));
+                    ax[2 * h + 1] = fmaf(lc, v.z, fmaf(-ls, v.w, lx));
+                    ay[2 * h + 1] = fmaf(ls, v.z, fmaf(lc, v.w, ly));
+                    ln[6 * h] = fmaf(lc, n.x, -ls * n.y);
+                    ln[6 * h + 1] = fmaf(ls, n.x, lc * n.y);
+                    ln[6 * h + 3] = fmaf(lc, n.z, -ls * n.w);
+                    ln[6 * h + 4] = fmaf(ls, n.z, lc * n.w);
+                }
+#pragma unroll
+                for (int e = 0; e < VA; e++)       // line offset; an edge beyond nv never separates
+                    ln[3 * e + 2] = (e < nv) ? fmaf(ln[3 * e], ax[e], ln[3 * e + 1] * ay[e]) : BIG;
+                __syncwarp();                       // previous group's readers are done with sA
+#pragma unroll
+                for (int h = 0; h < VA / 2; h++) sA[h * 32 + lane] = make_float4(ax[2 * h], ax[2 * h + 1], ay[2 * h], ay[2 * h + 1]);
+#pragma unroll
+                for (int h = 0; h < (VA * 3 + 3) / 4; h++)
+                    sA[(VA / 2 + h) * 32 + lane] = make_float4(ln[4 * h], ln[4 * h + 1], ln[4 * h + 2], ln[4 * h + 3]);
+                __syncwarp();
+            }
+            const float acx = active ? fmaf(lc, cc.x, fmaf(-ls, cc.y, lx)) : -FAR;
+            const float acy = active ? fmaf(ls, cc.x, fmaf(lc, cc.y, ly)) : -FAR;
+            const float arr = cc.z + 2.0f * tau;
+
+            bool collide = (s_coll[g] >> lane) & 1u;
+            bool par = false, punc = false;
+            unsigned qn = 0;                        // entries in this warp's queue (warp-uniform)
+            // bounding box of the warp's 32 polygon centres: decides which 32-blocks of the spatially sorted obstacle
+            // slots / boundary segments can matter for anyone in the warp
+            const bool cull_o = !NOCULL && nslot > 32, cull_s = !NOCULL && nseg > 32;
+            float wx0 = 0.f, wx1 = 0.f, wy0 = 0.f, wy1 = 0.f, wr = 0.f;
+            if (cull_o || cull_s) {
+                wx0 = warp_min(active ? acx : BIG); wx1 = warp_max(active ? acx : -BIG);
+                wy0 = warp_min(active ? acy : BIG); wy1 = warp_max(active ? acy : -BIG);
+                wr = warp_max(active ? arr : 0.f);
+            }
+
+            if (ph == 0) {   // statistic: nominal pair count of this tile
+                unsigned w = __reduce_add_sync(FULL, active ? (unsigned)(nobst + nseg) : 0u);
+                if (lane == 0 && w) atomicAdd(&p.cnt->pairs_nominal, (unsigned long long)w);
+            }
+
+            // queue entry = (owner lane << 16) | record index in the tile.  Draining evaluates up to 32 queued pairs at
+            // once, one per lane, whichever lane they belong to: the full separating-axis test runs with all lanes busy
+            // although only ~1 % of the pairs reach it.
+            auto push_hits = [&](unsigned &hits, int base, auto &&drain) {
+                while (__any_sync(FULL, hits != 0)) {
+                    if (qn >= 32) drain();
+                    const bool has = hits != 0;
+                    const unsigned bal = __ballot_sync(FULL, has);
+                    if (has) {
+                        const int k = __clz(hits);
+                        hits &= ~(0x80000000u >> k);
+                        sq[qn + __popc(bal & lt_mask)] = ((unsigned)lane << 16) | (unsigned)(base + k);
+                    }
+                    qn += __popc(bal);
+                    __syncwarp();
+                    if (collide && !noexit) hits = 0;
+                }
+            };
+            auto pop_batch = [&](unsigned &ent) -> bool {       // take min(32, qn) entries, compact the rest
+                const int n = min(32u, qn);
+                const bool have = lane < n;
+                ent = have ? sq[lane] : 0u;
+                unsigned rest = (lane + 32 < (int)qn) ? sq[lane + 32] : 0u;
+                __syncwarp();
+                if (lane + 32 < (int)qn) sq[lane] = rest;
+                __syncwarp();
+                qn -= n;
+                return have;
+            };
+            auto drain_obst = [&]() {
+                unsigned ent;
+                const bool have = pop_batch(ent);
+                const int src = ent >> 16, slot = ent & 0xffff;
+                float sep = BIG;
+                if (have) {
+                    PolyRegs<VA> A;
+                    PolyRegs<VB> B;
+                    A.load(sA, 32, src);
+                    B.load(s_ob, p.cap_o, slot);
+                    sep = sat_polys<VA, VB>(A, B);
+                    if (COUNT) n_axis++;
+                }
+                const bool hit = have && sep < -tau;
+                if (have && !hit && !(sep > tau)) push_work(p, q, (gbeg + g) * 32 + src, j, KIND_OBST, o0 + oc0 + slot);
+                const unsigned m = __reduce_or_sync(FULL, hit ? (1u << src) : 0u);
+                collide |= (m >> lane) & 1u;
+            };
+            auto drain_seg = [&]() {
+                unsigned ent;
+                const bool have = pop_batch(ent);
+                const int src = ent >> 16, k = ent & 0xffff;
+                float sep = BIG;
+                if (have) {
+                    PolyRegs<VA> A;
+                    A.load(sA, 32, src);
+                    sep = sat_segment<VA>(A, s_sg[k], s_sg[p.cap_s + k]);
+                    if (COUNT) n_axis++;
+                }
+                const bool hit = have && sep < -tau;
+                if (have && !hit && !(sep > tau)) push_work(p, q, (gbeg + g) * 32 + src, j, KIND_SEG, g0 + sc0 + k);
+                const unsigned m = __reduce_or_sync(FULL, hit ? (1u << src) : 0u);
+                collide |= (m >> lane) & 1u;
+            };
+
+            // ---- obstacles of this time step --------------------------------------------------------------------
+            if (NOCULL) {
+                // full evaluation: every lane runs the complete test against every obstacle of the step
+                PolyRegs<VA> A;
+                A.load(sA, 32, lane);
+                for (int k = 0; k < min(ocn, nobst - oc0); k++) {
+                    PolyRegs<VB> B;
+                    B.load(s_ob, p.cap_o, k);
+                    const float sep = sat_polys<VA, VB>(A, B);
+                    if (active) {
+                        if (COUNT) n_axis++;
+                        if (sep < -tau) collide = true;
+                        else if (!(sep > tau)) push_work(p, q, ci, j, KIND_OBST, o0 + oc0 + k);
+                    }
+                    if (!noexit && (k & 31) == 31 && __all_sync(FULL, collide || !active)) break;
+                }
+            } else {
+                const float4 *s_cx4 = reinterpret_cast<const float4 *>(s_c);
+                const float4 *s_cy4 = reinterpret_cast<const float4 *>(s_c + p.cap_o);
+                const float4 *s_cr4 = reinterpret_cast<const float4 *>(s_c + 2 * p.cap_o);
+                const f32x2 nax = pack2(-acx, -acx), nay = pack2(-acy, -acy);
+                // which blocks of 32 slots can matter: lane b tests block b (one load latency for the whole tile).  A
+                // block whose circles (box already inflated by their radii) cannot come within rcull of any centre of
+                // this warp has every pair separated on the box axis.
+                unsigned live_o = FULL;
+                if (cull_o) {
+                    const int nblk = ocn >> 5;               // <= 10 (cap_o <= 320)
+                    bool live = false;
+                    if (lane < nblk) {
+                        const float4 bb = __ldg(p.ob_box + ((o0 + oc0) >> 5) + lane);
+                        live = !(bb.x > wx1 + rcull || bb.z < wx0 - rcull || bb.y > wy1 + rcull || bb.w < wy0 - rcull);
+                    }
+                    live_o = __ballot_sync(FULL, live);
+                }
+                for (int ob = 0; ob < ocn; ob += 32) {
+                    if (!((live_o >> (ob >> 5)) & 1u)) {
+                        if (COUNT && active) n_skip += min(32, nobst - oc0 - ob);
+                        continue;
+                    }
+                    // axis 0: centre line with bounding radii.  Three warp-broadcast LDS.128 bring four obstacles; packed
+                    // FADD2/FFMA2 evaluate e = |dc|^2 - (rb + rcull)^2 for two of them per instruction and the sign bit
+                    // of e is shifted into the hit word (bit 31-k <-> slot ob+k).
+                    unsigned hits = 0;
+#pragma unroll
+                    for (int qd = 0; qd < 8; qd++) {
+                        const float4 X = s_cx4[(ob >> 2) + qd], Y = s_cy4[(ob >> 2) + qd], R = s_cr4[(ob >> 2) + qd];
+                        const f32x2 dx01 = add2(pack2(X.x, X.y), nax), dy01 = add2(pack2(Y.x, Y.y), nay);
+                        const f32x2 dx23 = add2(pack2(X.z, X.w), nax), dy23 = add2(pack2(Y.z, Y.w), nay);
+                        const f32x2 e01 = fma2(dx01, dx01, fma2(dy01, dy01, pack2(R.x, R.y)));
+                        const f32x2 e23 = fma2(dx23, dx23, fma2(dy23, dy23, pack2(R.z, R.w)));
+                        hits = __funnelshift_l((unsigned)e01, hits, 1);
+                        hits = __funnelshift_l((unsigned)(e01 >> 32), hits, 1);
+                        hits = __funnelshift_l((unsigned)e23, hits, 1);
+                        hits = __funnelshift_l((unsigned)(e23 >> 32), hits, 1);
+                    }
+                    if (!active || (collide && !noexit)) hits = 0;
+                    if (COUNT && active) n_cull += min(32, nobst - oc0 - ob);
+                    push_hits(hits, ob, drain_obst);
+                    if (qn >= 32) {
+                        drain_obst();
+                        if (!noexit && __all_sync(FULL, collide || !active)) { qn = 0; break; }   // warp-wide early exit
+                    }
+                }
+                while (qn) drain_obst();
+            }
+
+            // ---- boundary segments of the free space at this time step -----------------------------------------
+            if (scn && (noexit || !__all_sync(FULL, collide || !active))) {
+                const bool blockcull = cull_s;        // a single block cannot be skipped: no box work
+                const float4 *boxes = p.sg_box + ((g0 + sc0) >> 5);
+                // the even-odd ray may run along +x, -x, +y or -y; take the direction whose ray corridor meets the
+                // fewest blocks of the whole range (a road aligned with the ray would otherwise keep every block alive)
+                int dir = 0;
+                if (blockcull) {
+                    const float4 *all = p.sg_box + (g0 >> 5);
+                    const int nblk = (nseg + 31) >> 5;
+                    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+                    for (int b = lane; b < ((nblk + 31) & ~31); b += 32) {
+                        float4 bb = (b < nblk) ? __ldg(all + b) : make_float4(BIG, BIG, -BIG, -BIG);
+                        const bool iny = bb.w >= wy0 && bb.y <= wy1, inx = bb.z >= wx0 && bb.x <= wx1;
+                        c0 += __popc(__ballot_sync(FULL, iny && bb.z >= wx0));      // +x
+                        c1 += __popc(__ballot_sync(FULL, iny && bb.x <= wx1));      // -x
+                        c2 += __popc(__ballot_sync(FULL, inx && bb.w >= wy0));      // +y
+                        c3 += __popc(__ballot_sync(FULL, inx && bb.y <= wy1));      // -y
+                    }
+                    int best = c0;
+                    if (c1 < best) { best = c1; dir = 1; }
+                    if (c2 < best) { best = c2; dir = 2; }
+                    if (c3 < best) { best = c3; dir = 3; }
+                }
+                const bool ray_y = dir >= 2, flip = (dir == 1) || (dir == 2);
+                const float pc = ray_y ? acx : acy;          // coordinate the ray keeps constant
+                // live blocks of this phase (<= 16: cap_s <= 512), lane b tests block b
+                unsigned live_s = FULL;
+                if (blockcull) {
+                    bool live = false;
+                    if (lane < ((scn + 31) >> 5)) {
+                        const float4 bb = __ldg(boxes + lane);
+                        // a segment can meet a polygon only if the boxes overlap; it can be crossed by the ray of a
+                        // centre only if it reaches that centre's constant coordinate and is not entirely behind it
+                        const bool sat_rel = bb.x <= wx1 + wr && bb.z >= wx0 - wr && bb.y <= wy1 + wr && bb.w >= wy0 - wr;
+                        const bool iny = bb.w >= wy0 && bb.y <= wy1, inx = bb.z >= wx0 && bb.x <= wx1;
+                        const bool par_rel = dir == 0 ? (iny && bb.z >= wx0) : dir == 1 ? (iny && bb.x <= wx1)
+                                           : dir == 2 ? (inx && bb.w >= wy0) : (inx && bb.y <= wy1);
+                        live = sat_rel || par_rel;
+                    }
+                    live_s = __ballot_sync(FULL, live);
+                }
+                for (int sb = 0; sb < scn; sb += 32) {
+                    const int cnt = min(32, scn - sb);
+                    if (!((live_s >> (sb >> 5)) & 1u)) continue;
+                    unsigned hits = 0;
+#pragma unroll 2
+                    for (int k = 0; k < cnt; k++) {
+                        float4 sa = s_sg[sb + k], sl = s_sg[p.cap_s + sb + k];
+                        float dl = fmaf(sl.x, acx, fmaf(sl.y, acy, -sl.z));       // centre to the segment's line
+                        // even-odd crossing parity of the ray from the polygon centre.  The two comparisons are exact
+                        // on the float32 data and consistent between segments that share a vertex; the side test is
+                        // trusted only outside the error band
+                        const float ea = ray_y ? sa.x : sa.y, eb = ray_y ? sa.z : sa.w;
+                        bool ua = ea > pc, ub = eb > pc;
+                        if (ua != ub) {
+                            par ^= (ub != flip) ? (dl < 0.f) : (dl > 0.f);
+                            punc |= fabsf(dl) <= tau;
+                        }
+                        float tt = fmaf(-sl.y, acx - 0.5f * (sa.x + sa.z), sl.x * (acy - 0.5f * (sa.y + sa.w)));
+                        bool near = NOCULL ? (sl.w >= 0.f) : ((fabsf(dl) <= arr) & (fabsf(tt) <= sl.w + arr));
+                        if (near) hits |= 0x80000000u >> k;
+                    }
+                    if (!active || (collide && !noexit)) hits = 0;
+                    if (COUNT && active) n_cull += cnt;
+                    push_hits(hits, sb, drain_seg);
+                    if (qn >= 32) drain_seg();
+                }
+                while (qn) drain_seg();
+            }
+
+            // ---- fold this phase into the group state ----------------------------------------------------------
+            unsigned bc = __ballot_sync(FULL, collide), bp = __ballot_sync(FULL, par), bu = __ballot_sync(FULL, punc);
+            if (nphase > 1) {
+                if (lane == 0) { s_coll[g] |= bc; s_par[g] ^= bp; s_punc[g] |= bu; }
+                __syncwarp();
+                bc = s_coll[g]; bp = s_par[g]; bu = s_punc[g];
+            }
+            if (ph == nphase - 1) {
+                bool coll = (bc >> lane) & 1u;
+                if (has_region && active && !coll) {
+                    if ((bu >> lane) & 1u) push_work(p, q, ci, j, KIND_PARITY, 0);
+                    else if (!((bp >> lane) & 1u)) coll = true;        // centre outside the region
+                }
+                if (pos_base < 0) {
+                    unsigned word = __ballot_sync(FULL, coll && active);
+                    if (lane == 0 && word) atomicOr(p.mask + Q->mask_off + gbeg + g, word);
+                } else {        // spatially sorted candidate set: bits in sorted order, k_refine moves them home
+                    unsigned word = __ballot_sync(FULL, coll && active);
+                    if (lane == 0 && word) atomicOr(p.mask_sorted + Q->mask_off + gbeg + g, word);
+                }
+            }
+        }
+        if (nphase > 1) __syncthreads();      // everyone is done with the tile before the next bulk copy overwrites it
+    }
+    if (COUNT) {
+        n_cull = __reduce_add_sync(FULL, n_cull);
+        n_axis = __reduce_add_sync(FULL, n_axis);
+        n_skip = __reduce_add_sync(FULL, n_skip);
+        if (lane == 0) {
+            atomicAdd(&p.cnt->cull_tests, (unsigned long long)n_cull);
+            atomicAdd(&p.cnt->axis_tests, (unsigned long long)n_axis);
+            atomicAdd(&p.cnt->box_skipped, (unsigned long long)n_skip);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// float64 / exact refinement of the pairs inside the float32 band
+// ---------------------------------------------------------------------------------------------------------------------
+// One WARP per work-list item: the orientation tests of an item (up to nA*nB of them per direction) are independent,
+// so the lanes split them and votes put the answer together.  A single thread needs ~20 k cycles per polygon pair
+// (dependent float64 chains, local-memory polygon arrays); a warp needs ~1-2 k, which is what a planner that waits on
+// every query cares about.
+__global__ void __launch_bounds__(128) k_refine(const KParams p) {
+    __shared__ double s_pts[4][2 * (MPC_MAX_LIB_VERTS + MPC_MAX_OBST_VERTS)];
+    const unsigned n = min(p.cnt->wl_count, (unsigned)p.wl_cap);
+    const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+    double *Ax = s_pts[wib], *Ay = Ax + MPC_MAX_LIB_VERTS, *Bx = Ay + MPC_MAX_LIB_VERTS, *By = Bx + MPC_MAX_OBST_VERTS;
+    unsigned refined = 0, ties = 0, near_t = 0, par_ref = 0;
+    const bool strict = p.mode & MPC_MODE_VALIDATOR;
+    // phase A: result bits of spatially sorted candidate sets go home to the caller's candidate order: one thread per
+    // mask word (its query found by bisection on the mask offsets), only set bits cost an atomic
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < p.nwords; w += gridDim.x * blockDim.x) {
+        unsigned bits = p.mask_sorted[w];
+        if (!bits) continue;
+        int lo = 0, hi = p.B;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (p.q[mid].mask_off <= w) lo = mid; else hi = mid;
+        }
+        while (lo + 1 < p.B && p.q[lo + 1].mask_off <= w) lo++;          // queries without candidates share an offset
+        const QDev *Q = p.q + lo;
+        const int base = Q->pos_base + (w - Q->mask_off) * 32;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int oi = __ldg(p.cand_pos + base + b);
+            atomicOr(p.mask + Q->mask_off + (oi >> 5), 1u << (oi & 31));
+        }
+    }
+    for (unsigned item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n; item += warps) {
+        const int4 e = p.wl[item];
+        const int q = e.x, ci = e.y, j = e.z & 0xffff, kind = e.z >> 16, obj = e.w;
+        const QDev *Q = p.q + q;
+        const int pj = p.cand[Q->cand_base + ci] * p.J + j;
+        const int nA = p.lib_nv[pj];
+        __syncwarp();
+        if ((int)lane < nA) {
+            const double *lv = p.lib_v64 + ((size_t)pj * p.lib_vmax + lane) * 2;
+            // shapely affine_transform(o['space'], [cos, -sin, sin, cos, x, y]): xp = a*x + b*y + xoff, left to right
+            Ax[lane] = __dadd_rn(__dadd_rn(__dmul_rn(Q->c, lv[0]), __dmul_rn(-Q->s, lv[1])), Q->x);
+            Ay[lane] = __dadd_rn(__dadd_rn(__dmul_rn(Q->s, lv[0]), __dmul_rn(Q->c, lv[1])), Q->y);
+        }
+        bool collide = false;
+        if (kind == KIND_OBST) {
+            const int nB = p.ob_nv[obj];
+            if ((int)lane < nB) {
+                const double *bv = p.ob_v64 + ((size_t)obj * p.ob_vmax + lane) * 2;
+                Bx[lane] = bv[0]; By[lane] = bv[1];
+            }
+            __syncwarp();
+            // an edge separates iff none of the other polygon's vertices is on its inner side (strict: or on it)
+            unsigned badA = 0, badB = 0;       // bit e set: edge e of A (of B) does not separate
+            for (int c = lane; c < ((nA * nB + 31) & ~31); c += 32) {
+                bool bad = false, bad2 = false;
+                int ea = 0, eb = 0;
+                if (c < nA * nB) {
+                    ea = c / nB;
+                    const int k = c - ea * nB, e1 = (ea + 1 == nA) ? 0 : ea + 1;
+                    if (Ax[ea] == Ax[e1] && Ay[ea] == Ay[e1]) bad = true;
+                    else {
+                        const int o = orient2d(Ax[ea], Ay[ea], Ax[e1], Ay[e1], Bx[k], By[k], ties);
+                        bad = strict ? (o >= 0) : (o > 0);
+                    }
+                    eb = c / nA;
+                    const int k2 = c - eb * nA, f1 = (eb + 1 == nB) ? 0 : eb + 1;
+                    if (Bx[eb] == Bx[f1] && By[eb] == By[f1]) bad2 = true;
+                    else {
+                        const int o = orient2d(Bx[eb], By[eb], Bx[f1], By[f1], Ax[k2], Ay[k2], ties);
+                        bad2 = strict ? (o >= 0) : (o > 0);
+                    }
+                }
+                badA |= __reduce_or_sync(FULL, bad ? (1u << ea) : 0u);
+                badB |= __reduce_or_sync(FULL, bad2 ? (1u << eb) : 0u);
+            }
+            const bool sepA = (~badA & ((1u << nA) - 1u)) != 0, sepB = (~badB & ((1u << nB) - 1u)) != 0;
+            collide = !(sepA || sepB);
+            // near-tangent statistic: |separation| < 1e-9 m, one edge per lane
+            double mine = -1e300;
+            if ((int)lane < nA + nB) {
+                const bool fromA = (int)lane < nA;
+                const int ee = fromA ? lane : lane - nA, nn = fromA ? nA : nB, e1 = (ee + 1 == nn) ? 0 : ee + 1;
+                const double *Px = fromA ? Ax : Bx, *Py = fromA ? Ay : By, *Qx = fromA ? Bx : Ax, *Qy = fromA ? By : Ay;
+                const int nq = fromA ? nB : nA;
+                const double ex = Px[e1] - Px[ee], ey = Py[e1] - Py[ee], len = sqrt(ex * ex + ey * ey);
+                if (len > 0.0) {
+                    double mn = 1e300;
+                    for (int k = 0; k < nq; k++) mn = fmin(mn, ey * (Qx[k] - Px[ee]) - ex * (Qy[k] - Py[ee]));
+                    mine = mn / len;
+                }
+            }
+            for (int o = 16; o; o >>= 1) mine = fmax(mine, __shfl_xor_sync(FULL, mine, o));
+            if (lane == 0) { if (fabs(mine) < 1e-9) near_t++; refined++; }
+        } else if (kind == KIND_SEG) {
+            __syncwarp();
+            const double *sg = p.sg_64 + 4 * (size_t)obj;
+            const double s0x = sg[0], s0y = sg[1], s1x = sg[2], s1y = sg[3];
+            // lanes 0..nA-1: edge i of the polygon against both end points; lanes 16..16+nA-1: vertex against the line
+            bool excl = false, pos = false, neg = false;
+            if ((int)lane < nA) {
+                const int i = lane, k = (i + 1 == nA) ? 0 : i + 1;
+                if (!(Ax[i] == Ax[k] && Ay[i] == Ay[k]))
+                    excl = orient2d(Ax[i], Ay[i], Ax[k], Ay[k], s0x, s0y, ties) <= 0 &&
+                           orient2d(Ax[i], Ay[i], Ax[k], Ay[k], s1x, s1y, ties) <= 0;
+            } else if (lane >= 16 && (int)lane - 16 < nA) {
+                const int o = orient2d(s0x, s0y, s1x, s1y, Ax[lane - 16], Ay[lane - 16], ties);
+                pos = o > 0; neg = o < 0;
+            }
+            const bool any_excl = __any_sync(FULL, excl), any_pos = __any_sync(FULL, pos), any_neg = __any_sync(FULL, neg);
+            const bool point = (s0x == s1x && s0y == s1y);
+            collide = !any_excl && (point || (any_pos && any_neg));
+            if (lane == 0) refined++;
+        } else {
+            __syncwarp();
+            double cx = 0.0, cy = 0.0;
+            for (int k = 0; k < nA; k++) { cx += Ax[k]; cy += Ay[k]; }
+            cx /= nA; cy /= nA;
+            const int step = Q->step0 + Q->t0 + p.slot_t[j];
+            const int g0 = p.step_seg_begin[step], g1 = p.step_seg_end[step];
+            bool inside = false, on_edge = false;
+            for (int g = g0 + (int)lane; g < g1; g += 32) {
+                const double *sg = p.sg_64 + 4 * (size_t)g;
+                const double sax = sg[0], say = sg[1], sbx = sg[2], sby = sg[3];
+                if (sax == sbx && say == sby) continue;
+                const int o = orient2d(sax, say, sbx, sby, cx, cy, ties);
+                if (o == 0 && fmin(sax, sbx) <= cx && cx <= fmax(sax, sbx) && fmin(say, sby) <= cy && cy <= fmax(say, sby))
+                    on_edge = true;
+                if ((say > cy) != (sby > cy)) {
+                    if ((sby > say && o > 0) || (sby < say && o < 0)) inside = !inside;
+                }
+            }
+            const unsigned odd = __popc(__ballot_sync(FULL, inside)) & 1u;
+            collide = __any_sync(FULL, on_edge) || !odd;
+            if (lane == 0) par_ref++;
+        }
+        if (lane == 0 && collide) {
+            const int oi = Q->pos_base >= 0 ? p.cand_pos[Q->pos_base + ci] : ci;
+            atomicOr(p.mask + Q->mask_off + (oi >> 5), 1u << (oi & 31));
+        }
+    }
+    refined = __reduce_add_sync(FULL, refined);
+    ties = __reduce_add_sync(FULL, ties);
+    near_t = __reduce_add_sync(FULL, near_t);
+    par_ref = __reduce_add_sync(FULL, par_ref);
+    if (lane == 0) {
+        if (refined) atomicAdd(&p.cnt->refined, (unsigned long long)refined);
+        if (ties) atomicAdd(&p.cnt->exact_ties, (unsigned long long)ties);
+        if (near_t) atomicAdd(&p.cnt->near_tangent, (unsigned long long)near_t);
+        if (par_ref) atomicAdd(&p.cnt->parity_refined, (unsigned long long)par_ref);
+    }
+}
+
+__global__ void k_fill_u32(unsigned *p, size_t n, unsigned v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace mpc

@@ -1,6 +1,6 @@
 """Host-side handle of the device-resident collision checker (one per GPU).
 
-Thin numpy <-> C-ABI glue; every geometric decision is made by the CUDA kernels in csrc/mpc_kernels.cu.
+Thin numpy <-> C-ABI glue; every geometric decision is made by the CUDA kernels in csrc/mpc_device.cuh.
 Reference being replaced: the per-occupancy shapely loop of ``collision_check``
 (src/lowLevelPlannerManeuverAutomaton.py:95-125) and ``collisionChecker`` (auxiliary/collisionChecker.py:6-35).
 """
