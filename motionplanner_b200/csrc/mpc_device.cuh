@@ -169,7 +169,7 @@ template <int VB>
 __global__ void __launch_bounds__(256) k_order_obst(const double *__restrict__ src64, const int *__restrict__ src_nv,
                                                     const int *__restrict__ src_off, const int *__restrict__ slot_off,
                                                     const int *__restrict__ scene_step_off, int nscenes,
-                                                    const double *__restrict__ origins, int *__restrict__ order) {
+                                                    const double *__restrict__ origins, int *__restrict__ order, int vsrc) {
     __shared__ unsigned s_key[SORT_MAX];
     __shared__ int s_idx[SORT_MAX];
     const int step = blockIdx.x;
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) k_order_obst(const double *__restrict__ s
         unsigned key = 0xffffffffu;
         if (i < cnt) {
             const int nv = src_nv[o0 + i];
-            const double *v = src64 + (size_t)(o0 + i) * VB * 2;
+            const double *v = src64 + (size_t)(o0 + i) * vsrc * 2;   // caller's vertex stride
             double cx = 0.0, cy = 0.0;
             for (int k = 0; k < nv && k < VB; k++) { cx += v[2 * k]; cy += v[2 * k + 1]; }
             if (nv > 0) { cx = cx / nv - ox; cy = cy / nv - oy; }
@@ -226,7 +226,7 @@ __global__ void k_stage_obst(int nslots, const double *__restrict__ src64, const
                              const int *__restrict__ order, const int *__restrict__ slot_off, int nsteps,
                              const int *__restrict__ scene_step_off, int nscenes, const double *__restrict__ origins,
                              float4 *__restrict__ ob_f, float *__restrict__ ob_c, float4 *__restrict__ ob_box,
-                             double *__restrict__ ob64, int *__restrict__ ob_nv, int stride, float *maxabs) {
+                             double *__restrict__ ob64, int *__restrict__ ob_nv, int stride, float *maxabs, int vsrc) {
     int slot = blockIdx.x * blockDim.x + threadIdx.x;     // nslots is a multiple of 32: whole warps are in range
     if (slot >= nslots) return;
     constexpr int F = ob_fields(VB);
@@ -239,7 +239,7 @@ __global__ void k_stage_obst(int nslots, const double *__restrict__ src64, const
     bool ok = nv >= 3 && nv <= VB;
     double x[VB], y[VB];
     if (ok) {
-        const double *sv = src64 + (size_t)o * VB * 2;
+        const double *sv = src64 + (size_t)o * vsrc * 2;
         for (int k = 0; k < VB; k++) { x[k] = sv[2 * (k < nv ? k : nv - 1)]; y[k] = sv[2 * (k < nv ? k : nv - 1) + 1]; }
         double area = 0.0;
         for (int k = 0; k < nv; k++) {

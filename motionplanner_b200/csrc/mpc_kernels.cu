@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -423,6 +424,9 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     if (nscenes <= 0 || !scene_step_off || !origins || !step_obst_off || !step_seg_begin || !step_seg_end)
         return fail(ctx, MPC_E_ARG, "bad scene arguments");
     CU(cudaSetDevice(ctx->device));
+    const bool dbg_t = getenv("MPC_DEBUG_TIMING") != nullptr;
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) { if (dbg_t) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[mpc set_scenes] %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - T0).count()); T0 = t; } };
     const int nsteps = scene_step_off[nscenes];
     if (scene_step_off[0] != 0 || nsteps < 0) return fail(ctx, MPC_E_ARG, "scene_step_off must start at 0");
     for (int s = 0; s < nscenes; s++)
@@ -436,11 +440,13 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     // ---- boundary segments: every distinct [begin, end) range becomes a 32-aligned, spatially sorted (Morton order of
     // the midpoints) block range on the device, so that k_check can skip whole blocks by their bounding box
     int max_o = 0, max_s = 0;
-    std::map<std::pair<int, int>, std::pair<int, int>> ranges;        // (begin, end) -> (device begin, scene)
+    struct SegJob { int b, e, scene, start; };
+    std::vector<SegJob> jobs;                                         // one per distinct range (pass 2 sorts them)
+    std::map<std::pair<int, int>, int> ranges;                        // (begin, end) -> job
     std::vector<int> dev_begin(std::max(nsteps, 1), -1), dev_end(std::max(nsteps, 1), -1);
-    std::vector<double> dsegs;
-    std::vector<int> dscene;
-    for (int s = 0; s < nscenes; s++)
+    int nslots_acc = 0;
+    for (int s = 0; s < nscenes; s++) {
+        int last_b = -2, last_e = -2, last_job = -1;                  // consecutive steps usually share their range
         for (int k = scene_step_off[s]; k < scene_step_off[s + 1]; k++) {
             int no = step_obst_off[k + 1] - step_obst_off[k];
             if (no < 0) return fail(ctx, MPC_E_ARG, "step_obst_off not monotone at step %d", k);
@@ -449,37 +455,25 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
             if (b < 0) continue;
             if (e < b || e > nseg) return fail(ctx, MPC_E_ARG, "segment range of step %d outside 0..%d", k, nseg);
             max_s = std::max(max_s, e - b);
-            auto key = std::make_pair(b, e);
-            auto it = ranges.find(key);
-            if (it != ranges.end() && it->second.second != s) it = ranges.end();   // same range, other origin: copy
-            if (it == ranges.end()) {
-                const int n = e - b, start = (int)dscene.size();
-                std::vector<std::pair<unsigned, int>> order(n);
-                double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
-                for (int g = b; g < e; g++) {
-                    double mx = 0.5 * (segs[4 * g] + segs[4 * g + 2]), my = 0.5 * (segs[4 * g + 1] + segs[4 * g + 3]);
-                    x0 = std::min(x0, mx); x1 = std::max(x1, mx); y0 = std::min(y0, my); y1 = std::max(y1, my);
+            int job = -1;
+            if (b == last_b && e == last_e) job = last_job;
+            else {
+                auto it = ranges.find({b, e});
+                if (it != ranges.end() && jobs[it->second].scene == s) job = it->second;
+                else {                                                // new range (or same range under another origin)
+                    job = (int)jobs.size();
+                    jobs.push_back({b, e, s, nslots_acc});
+                    nslots_acc += (e - b + 31) / 32 * 32;
+                    ranges[{b, e}] = job;
                 }
-                const double sx = (x1 > x0) ? 65535.0 / (x1 - x0) : 0.0, sy = (y1 > y0) ? 65535.0 / (y1 - y0) : 0.0;
-                for (int g = b; g < e; g++) {
-                    double mx = 0.5 * (segs[4 * g] + segs[4 * g + 2]), my = 0.5 * (segs[4 * g + 1] + segs[4 * g + 3]);
-                    order[g - b] = {morton16((unsigned)((mx - x0) * sx), (unsigned)((my - y0) * sy)), g};
-                }
-                std::sort(order.begin(), order.end());
-                const int padded = (n + 31) / 32 * 32;
-                dsegs.resize((size_t)(start + padded) * 4, 0.0);
-                dscene.resize((size_t)(start + padded), -1);
-                for (int i = 0; i < n; i++) {
-                    const int g = order[i].second;
-                    for (int c = 0; c < 4; c++) dsegs[(size_t)(start + i) * 4 + c] = segs[4 * g + c];
-                    dscene[start + i] = s;
-                }
-                it = ranges.insert_or_assign(key, std::make_pair(start, s)).first;
             }
-            dev_begin[k] = it->second.first;
-            dev_end[k] = it->second.first + (e - b);
+            last_b = b; last_e = e; last_job = job;
+            dev_begin[k] = jobs[job].start;
+            dev_end[k] = jobs[job].start + (e - b);
         }
-    const int nslots = (int)dscene.size();
+    }
+    lap("pass 1 (ranges)");
+    const int nslots = nslots_acc;
     int vmax_used = 3;
     for (int o = 0; o < nobst; o++) {
         if (obst_nv[o] > Vo || obst_nv[o] < 0) return fail(ctx, MPC_E_ARG, "obst_nv[%d]=%d outside 0..%d", o, obst_nv[o], Vo);
@@ -495,7 +489,7 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     }
     const int noslots = slot_off[nsteps];
     const int ob_stride = std::max(noslots, 32), sg_stride = std::max(nslots, 32);
-    CU(ensure(ctx, ctx->ob_src, (size_t)std::max(nobst, 1) * VB * 2 * sizeof(double)));
+    CU(ensure(ctx, ctx->ob_src, (size_t)std::max(nobst, 1) * Vo * 2 * sizeof(double)));
     CU(ensure(ctx, ctx->ob_src_nv, (size_t)std::max(nobst, 1) * sizeof(int)));
     CU(ensure(ctx, ctx->ob_in, (size_t)ob_stride * VB * 2 * sizeof(double)));
     CU(ensure(ctx, ctx->ob_nv, (size_t)ob_stride * sizeof(int)));
@@ -505,6 +499,7 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     CU(ensure(ctx, ctx->ob_order, (size_t)ob_stride * sizeof(int)));
     CU(ensure(ctx, ctx->sg_f, (size_t)sg_stride * 2 * sizeof(float4)));
     CU(ensure(ctx, ctx->sg_box, (size_t)(sg_stride / 32 + 1) * sizeof(float4)));
+    lap("validate + ensure");
     cudaStream_t st = ctx->stream;
     // the small per-scene arrays travel as one packed block (one driver call instead of nine)
     {
@@ -525,7 +520,39 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
         CU(ensure(ctx, ctx->meta, off));
         char *h = (char *)ctx->h_meta, *d = (char *)ctx->meta.p;
         memcpy(h + o_org, origins, n_org);
-        if (nslots) memcpy(h + o_sg, dsegs.data(), (size_t)nslots * 4 * sizeof(double));
+        {   // pass 2: sort every distinct range along a Morton curve of the segment midpoints, straight into the block
+            double *dsegs = (double *)(h + o_sg);
+            int *dscene = (int *)(h + o_ss);
+            const int njobs = (int)jobs.size();
+#pragma omp parallel for schedule(dynamic, 4) if (njobs > 8)
+            for (int jb = 0; jb < njobs; jb++) {
+                const SegJob &J = jobs[jb];
+                const int n = J.e - J.b, padded = (n + 31) / 32 * 32;
+                std::vector<std::pair<unsigned, int>> order(n);
+                double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+                for (int g = J.b; g < J.e; g++) {
+                    double mx = 0.5 * (segs[4 * g] + segs[4 * g + 2]), my = 0.5 * (segs[4 * g + 1] + segs[4 * g + 3]);
+                    x0 = std::min(x0, mx); x1 = std::max(x1, mx); y0 = std::min(y0, my); y1 = std::max(y1, my);
+                }
+                const double sx = (x1 > x0) ? 65535.0 / (x1 - x0) : 0.0, sy = (y1 > y0) ? 65535.0 / (y1 - y0) : 0.0;
+                for (int g = J.b; g < J.e; g++) {
+                    double mx = 0.5 * (segs[4 * g] + segs[4 * g + 2]), my = 0.5 * (segs[4 * g + 1] + segs[4 * g + 3]);
+                    order[g - J.b] = {morton16((unsigned)((mx - x0) * sx), (unsigned)((my - y0) * sy)), g};
+                }
+                std::sort(order.begin(), order.end());
+                for (int i = 0; i < padded; i++) {
+                    double *dst = dsegs + (size_t)(J.start + i) * 4;
+                    if (i < n) {
+                        const double *src = segs + 4 * (size_t)order[i].second;
+                        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+                        dscene[J.start + i] = J.scene;
+                    } else {
+                        dst[0] = dst[1] = dst[2] = dst[3] = 0.0;
+                        dscene[J.start + i] = -1;
+                    }
+                }
+            }
+        }
         memcpy(h + o_sso, scene_step_off, n_sso);
         memcpy(h + o_slot, slot_off.data(), n_st1);
         memcpy(h + o_src, step_obst_off, n_st1);
@@ -534,7 +561,7 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
             memcpy(h + o_sb, dev_begin.data(), (size_t)nsteps * 4);
             memcpy(h + o_se, dev_end.data(), (size_t)nsteps * 4);
         }
-        if (nslots) memcpy(h + o_ss, dscene.data(), (size_t)nslots * 4);
+        lap("pack meta (pass 2)");
         CU(cudaMemcpyAsync(d, h, off, cudaMemcpyHostToDevice, st));
         ctx->origins_d.p = d + o_org; ctx->sg_64.p = d + o_sg; ctx->scene_step_off_d.p = d + o_sso;
         ctx->step_obst_off.p = d + o_slot; ctx->ob_src_off.p = d + o_src; ctx->step_obst_cnt.p = d + o_cnt;
@@ -544,30 +571,26 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     }
     CU(cudaMemsetAsync(ctx->maxabs.p, 0, sizeof(float), st));
     if (nobst) {
-        if (Vo == VB) {
-            CU(cudaMemcpyAsync(ctx->ob_src.p, obst, (size_t)nobst * VB * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-        } else {   // caller's vertex stride differs from the kernel's: repack rows
-            CU(cudaMemcpy2DAsync(ctx->ob_src.p, (size_t)VB * 2 * sizeof(double), obst, (size_t)Vo * 2 * sizeof(double),
-                                 (size_t)std::min(Vo, VB) * 2 * sizeof(double), nobst, cudaMemcpyHostToDevice, st));
-        }
+        // the caller's rows travel as they are (one contiguous DMA); the staging kernels read them with stride Vo
+        CU(cudaMemcpyAsync(ctx->ob_src.p, obst, (size_t)nobst * Vo * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(ctx->ob_src_nv.p, obst_nv, (size_t)nobst * sizeof(int), cudaMemcpyHostToDevice, st));
         int blocks = (noslots + 127) / 128;
         if (VB == 4) {
             k_order_obst<4><<<nsteps, 256, 0, st>>>((const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_src_off.p,
                                                     (const int *)ctx->step_obst_off.p, (const int *)ctx->scene_step_off_d.p, nscenes,
-                                                    (const double *)ctx->origins_d.p, (int *)ctx->ob_order.p);
+                                                    (const double *)ctx->origins_d.p, (int *)ctx->ob_order.p, Vo);
             k_stage_obst<4><<<blocks, 128, 0, st>>>(noslots, (const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_order.p,
                                                    (const int *)ctx->step_obst_off.p, nsteps, (const int *)ctx->scene_step_off_d.p, nscenes,
                                                    (const double *)ctx->origins_d.p, (float4 *)ctx->ob_f.p, (float *)ctx->ob_c.p, (float4 *)ctx->ob_box.p,
-                                                   (double *)ctx->ob_in.p, (int *)ctx->ob_nv.p, ob_stride, (float *)ctx->maxabs.p);
+                                                   (double *)ctx->ob_in.p, (int *)ctx->ob_nv.p, ob_stride, (float *)ctx->maxabs.p, Vo);
         } else {
             k_order_obst<8><<<nsteps, 256, 0, st>>>((const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_src_off.p,
                                                     (const int *)ctx->step_obst_off.p, (const int *)ctx->scene_step_off_d.p, nscenes,
-                                                    (const double *)ctx->origins_d.p, (int *)ctx->ob_order.p);
+                                                    (const double *)ctx->origins_d.p, (int *)ctx->ob_order.p, Vo);
             k_stage_obst<8><<<blocks, 128, 0, st>>>(noslots, (const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_order.p,
                                                    (const int *)ctx->step_obst_off.p, nsteps, (const int *)ctx->scene_step_off_d.p, nscenes,
                                                    (const double *)ctx->origins_d.p, (float4 *)ctx->ob_f.p, (float *)ctx->ob_c.p, (float4 *)ctx->ob_box.p,
-                                                   (double *)ctx->ob_in.p, (int *)ctx->ob_nv.p, ob_stride, (float *)ctx->maxabs.p);
+                                                   (double *)ctx->ob_in.p, (int *)ctx->ob_nv.p, ob_stride, (float *)ctx->maxabs.p, Vo);
         }
         CU(cudaGetLastError());
     }
@@ -576,9 +599,11 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
                                                          (float4 *)ctx->sg_f.p, sg_stride, (float4 *)ctx->sg_box.p, (float *)ctx->maxabs.p);
         CU(cudaGetLastError());
     }
+    lap("enqueue copies+kernels");
     float m = 0.f;
     CU(cudaMemcpyAsync(&m, ctx->maxabs.p, sizeof(float), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));      // host buffers (incl. the local staging vectors) may be reused after return
+    CU(cudaStreamSynchronize(st));
+    lap("device sync");      // host buffers (incl. the local staging vectors) may be reused after return
     ctx->maxabs_scene = m;
     ctx->nscenes = nscenes; ctx->nsteps = nsteps; ctx->nobst = nobst; ctx->nseg = nslots; ctx->sg_stride = sg_stride;
     ctx->ob_stride = ob_stride;
