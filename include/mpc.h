@@ -138,6 +138,34 @@ int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_off, con
 int mpc_query(mpc_ctx *ctx, int B, const mpc_query_desc *queries, const int32_t *cand_idx, int ncand, unsigned mode,
               uint32_t *out_mask, int mask_words, mpc_stats *stats);
 
+/* -- primitive-selection step: collision bits + child cost + goal test ------------------------------
+ * The reference creates every child of an expansion with expand_node (src/lowLevelPlannerManeuverAutomaton.py:192-214:
+ * x_ = T @ primitive.x + [x, y, 0, phi], cost = node.cost + np.sum((ref_traj[0:2, index] - x[0:2, index])**2)) and
+ * tests popped children with goal_check (:127-142: vehicle centre inside goal['space'] within its time window).
+ * mpc_expand returns both for all candidates of a batch together with the collision bits of mpc_query, in float64 and
+ * in the reference's operation order (numpy's BLAS fused multiply-add chain, numpy's pairwise summation over
+ * x0, y0, x1, y1, ...), so a search that orders its queue by these costs pops the same nodes as the reference.  The
+ * +1000 fixed-prefix penalty (:212) stays with the caller: it is search bookkeeping.
+ *
+ *   mpc_upload_trajectories  states [P][L][4] = primitive.x transposed (x, y, v, phi per step, rear-axle frame),
+ *                            nstates[P] = primitive.x.shape[1] (<= L <= 64); once per automaton
+ *   mpc_set_guidance         ref_xy [2][M] = ref_traj[0:2]; goals = param['goal'] (time window + boundary segments of
+ *                            goal['space'], seg_begin < 0 for None); b = param['b']; once per planning problem
+ *   mpc_expand               queries as for mpc_query with t0 = ind (index of the parent's last state) and (x, y, c, s)
+ *                            = node.x[0:2, -1], cos / sin of node.x[3, -1]; parent [B][2] = node.cost, node.x[3, -1].
+ *                            out_cost / out_goal_step [sum cand_cnt] in candidate order; goal step -1 = not reached. */
+typedef struct {
+    int32_t time_start, time_end;   /* goal['time_start'] <= i <= goal['time_end'] */
+    int32_t seg_begin, seg_end;     /* rows of goal_segs; seg_begin < 0: goal['space'] is None (always contained) */
+} mpc_goal;
+
+int mpc_upload_trajectories(mpc_ctx *ctx, const double *states, const int32_t *nstates, int P, int L);
+int mpc_set_guidance(mpc_ctx *ctx, const double *ref_xy, int M, const mpc_goal *goals, int ngoals,
+                     const double *goal_segs, int nseg, double b);
+int mpc_expand(mpc_ctx *ctx, int B, const mpc_query_desc *queries, const int32_t *cand_idx, int ncand,
+               const double *parent, unsigned mode, uint32_t *out_mask, int mask_words, double *out_cost,
+               int32_t *out_goal_step, mpc_stats *stats);
+
 /* -- measurement helpers (bench.py) ---------------------------------------------------------------------------------
  * mpc_prepare_query stages a query batch (H2D) without running it; mpc_run_prepared launches the kernels of the
  * staged batch `iters` times on the context's stream, optionally evicting L2 (writes a buffer larger than L2)

@@ -47,7 +47,11 @@ class MpcError(RuntimeError):
 _lib = None
 
 EXPORTS = ["mpc_create", "mpc_destroy", "mpc_last_error", "mpc_device_info", "mpc_upload_library", "mpc_set_scenes",
-           "mpc_query", "mpc_prepare_query", "mpc_run_prepared", "mpc_fetch_mask", "mpc_alloc_pinned", "mpc_free_pinned"]
+           "mpc_query", "mpc_prepare_query", "mpc_run_prepared", "mpc_fetch_mask", "mpc_alloc_pinned", "mpc_free_pinned",
+           "mpc_upload_trajectories", "mpc_set_guidance", "mpc_expand"]
+
+
+GOAL_DTYPE = np.dtype([("time_start", "<i4"), ("time_end", "<i4"), ("seg_begin", "<i4"), ("seg_end", "<i4")])
 
 
 def load():
@@ -75,6 +79,9 @@ def load():
     L.mpc_fetch_mask.argtypes = [vp, vp, i32]
     L.mpc_alloc_pinned.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
     L.mpc_free_pinned.argtypes = [vp, vp]
+    L.mpc_upload_trajectories.argtypes = [vp, vp, vp, i32, i32]
+    L.mpc_set_guidance.argtypes = [vp, vp, i32, vp, i32, vp, i32, C.c_double]
+    L.mpc_expand.argtypes = [vp, i32, vp, vp, i32, vp, u32, vp, i32, vp, vp, C.POINTER(Stats)]
     for name in EXPORTS:
         if name not in ("mpc_destroy", "mpc_last_error"):
             getattr(L, name).restype = i32

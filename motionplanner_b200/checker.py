@@ -270,6 +270,40 @@ class PrimitiveChecker:
         self._account(st, cnt * ns)
         return bits.reshape(ns, cnt).any(axis=0)
 
+    # -- primitive-selection step on the device --------------------------------------------------------
+    def enable_expand(self, ref_traj, goals, b):
+        """stage what mpc_expand needs: primitive trajectories (once per engine and automaton), the reference
+        trajectory and the goal sets of this planning problem.  `goals` is the reference's param['goal'] list."""
+        be = self.backend
+        key = (id(self.MA), len(self.MA.primitives))
+        if getattr(be, '_staged_trajectories', None) != key:
+            states, nstates = self.MA.trajectory_layout()
+            be.upload_trajectories(states, nstates)
+            be._staged_trajectories = key
+        rec, segs = goal_arrays(goals)
+        be.set_guidance(np.ascontiguousarray(ref_traj[0:2]), rec, segs, b)
+        self._pbuf = {}
+
+    def bucket_expand(self, x, y, phi, cost, t0, step_limit, bucket, scenes=(0,)):
+        """bucket_collides plus the cost expand_node gives every child and the step goal_check would return for it
+        (-1: goal not reached): (bits, cost, goal_step)"""
+        cnt = int(self._set_len[bucket])
+        ns = len(scenes)
+        q = self._qbuf.get(ns)
+        if q is None:
+            q = self._qbuf[ns] = make_queries(ns)
+            q['cand_off'] = 0
+        q['x'], q['y'], q['c'], q['s'] = x, y, np.cos(phi), np.sin(phi)
+        q['t0'], q['step_limit'], q['cand_set'], q['cand_cnt'] = t0, step_limit, bucket, cnt
+        q['scene'] = scenes
+        parent = self._pbuf.get(ns)
+        if parent is None:
+            parent = self._pbuf[ns] = np.zeros((ns, 2))
+        parent[:, 0], parent[:, 1] = cost, phi
+        bits, costs, goal, st = self.backend.expand(q, parent, None, self.mode)
+        self._account(st, cnt * ns)
+        return bits.reshape(ns, cnt).any(axis=0), costs[:cnt], goal[:cnt]
+
     def list_collides(self, x, y, phi, t0, step_limit, prim_indices, scenes=(0,)):
         """same for an explicit list of primitive indices"""
         idx = np.asarray(prim_indices, dtype=np.int32)
@@ -281,6 +315,22 @@ class PrimitiveChecker:
         bits, st = self.backend.query(q, idx, self.mode)
         self._account(st, len(idx) * len(scenes))
         return bits.reshape(len(scenes), len(idx)).any(axis=0)
+
+
+def goal_arrays(goals):
+    """param['goal'] (list of dicts with time_start, time_end, space) -> (GOAL_DTYPE records, boundary segments [n, 4])"""
+    from ._cabi import GOAL_DTYPE
+    rec = np.zeros(len(goals), GOAL_DTYPE)
+    parts, n = [], 0
+    for k, g in enumerate(goals):
+        if g['space'] is None:
+            rec[k] = (int(g['time_start']), int(g['time_end']), -1, -1)
+            continue
+        s = ring_segments(rings_of(g['space']))
+        rec[k] = (int(g['time_start']), int(g['time_end']), n, n + len(s))
+        parts.append(s)
+        n += len(s)
+    return rec, (np.concatenate(parts) if parts else np.zeros((0, 4)))
 
 
 def car_library(length, width):

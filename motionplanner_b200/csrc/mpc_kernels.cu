@@ -40,6 +40,7 @@
 
 #include "../../include/mpc.h"
 #include "mpc_device.cuh"
+#include "mpc_expand.cuh"
 
 // =====================================================================================================================
 // host side
@@ -98,6 +99,13 @@ struct mpc_ctx {
     size_t smem = 0;
     unsigned mode = 0;
     float maxabs_query = 0.f;
+    // primitive-selection step (mpc_expand): primitive trajectories, reference trajectory + goal sets
+    bool have_traj = false, have_guidance = false;
+    int tr_P = 0, tr_L = 0, g_M = 0, g_ngoals = 0, g_nseg = 0;
+    double g_b = 0.0;
+    DevBuf tr_states, tr_n, g_ref, g_goals, g_segs, e_pack, e_out;
+    void *h_exp = nullptr;
+    size_t h_exp_cap = 0;
 };
 
 static int fail(mpc_ctx *ctx, int code, const char *fmt, ...) {
@@ -141,7 +149,6 @@ static void invalidate_graphs(mpc_ctx *ctx) {
 static cudaError_t ensure_pinned(mpc_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->h_pin_cap) return cudaSuccess;
     invalidate_graphs(ctx);
-    for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     ctx->h_pin = nullptr;
     ctx->h_pin_cap = 0;
@@ -193,13 +200,15 @@ extern "C" void mpc_destroy(mpc_ctx *ctx) {
                       &ctx->sets_pos,
                       &ctx->ob_in, &ctx->ob_f, &ctx->ob_nv, &ctx->meta, &ctx->sg_f,
                       &ctx->sg_box, &ctx->maxabs, &ctx->qpack_d, &ctx->cand_d, &ctx->res_d, &ctx->wl,
-                      &ctx->flush};
+                      &ctx->flush, &ctx->tr_states, &ctx->tr_n, &ctx->g_ref, &ctx->g_goals, &ctx->g_segs, &ctx->e_pack,
+                      &ctx->e_out};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
+    if (ctx->h_exp) cudaFreeHost(ctx->h_exp);
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -902,14 +911,12 @@ static int run_graph(mpc_ctx *ctx, float *ms, bool timed) {
     return MPC_OK;
 }
 
-extern "C" int mpc_query(mpc_ctx *ctx, int B, const mpc_query_desc *queries, const int32_t *cand_idx, int ncand,
-                         unsigned mode, uint32_t *out_mask, int mask_words, mpc_stats *stats) {
-    int rc = prepare_host(ctx, B, queries, cand_idx, ncand, mode, false);
-    if (rc) return rc;
+// run the batch prepare_host() packed: graph replay for the common small-tile case, plain launches otherwise
+static int run_batch(mpc_ctx *ctx, uint32_t *out_mask, int mask_words, mpc_stats *stats) {
     if (mask_words != ctx->mask_words) return fail(ctx, MPC_E_ARG, "mask_words=%d but the batch needs %d", mask_words, ctx->mask_words);
     if (mask_words > 0 && !out_mask) return fail(ctx, MPC_E_ARG, "out_mask missing");
     float ms = 0.f;
-    int kernels = 2, overflow = 0;
+    int kernels = 2, overflow = 0, rc;
     if (ctx->smem > 48 * 1024) {          // large tiles need the opt-in attribute, which cannot be set during capture
         rc = issue_uploads(ctx);
         if (!rc) rc = run_once(ctx, &ms, &kernels, &overflow, stats != nullptr);
@@ -926,6 +933,13 @@ extern "C" int mpc_query(mpc_ctx *ctx, int B, const mpc_query_desc *queries, con
     if (mask_words) memcpy(out_mask, (const char *)ctx->h_res + sizeof(Counters), sizeof(unsigned) * (size_t)mask_words);
     fill_stats(ctx, stats, ms, kernels, overflow);
     return MPC_OK;
+}
+
+extern "C" int mpc_query(mpc_ctx *ctx, int B, const mpc_query_desc *queries, const int32_t *cand_idx, int ncand,
+                         unsigned mode, uint32_t *out_mask, int mask_words, mpc_stats *stats) {
+    int rc = prepare_host(ctx, B, queries, cand_idx, ncand, mode, false);
+    if (rc) return rc;
+    return run_batch(ctx, out_mask, mask_words, stats);
 }
 
 extern "C" int mpc_run_prepared(mpc_ctx *ctx, int iters, int flush_l2, float *ms_total, float *ms_main, mpc_stats *stats) {
@@ -971,4 +985,117 @@ extern "C" int mpc_fetch_mask(mpc_ctx *ctx, uint32_t *out_mask, int mask_words) 
         CU(cudaStreamSynchronize(ctx->stream));
     }
     return MPC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// primitive-selection step: collision bits + child cost + goal test in one call
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int mpc_upload_trajectories(mpc_ctx *ctx, const double *states, const int32_t *nstates, int P, int L) {
+    if (!ctx || !ctx->stream) return MPC_E_STATE;
+    if (!states || !nstates || P <= 0 || L <= 0) return fail(ctx, MPC_E_ARG, "bad trajectory arguments");
+    if (L > EXPAND_MAX_STATES) return fail(ctx, MPC_E_LIMIT, "L=%d exceeds %d states per primitive", L, EXPAND_MAX_STATES);
+    for (int p = 0; p < P; p++)
+        if (nstates[p] < 0 || nstates[p] > L) return fail(ctx, MPC_E_ARG, "nstates[%d]=%d outside 0..%d", p, nstates[p], L);
+    CU(cudaSetDevice(ctx->device));
+    ctx->have_traj = false;
+    CU(ensure(ctx, ctx->tr_states, sizeof(double) * 4 * (size_t)P * L));
+    CU(ensure(ctx, ctx->tr_n, sizeof(int) * (size_t)P));
+    CU(cudaMemcpyAsync(ctx->tr_states.p, states, sizeof(double) * 4 * (size_t)P * L, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->tr_n.p, nstates, sizeof(int) * (size_t)P, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->tr_P = P; ctx->tr_L = L;
+    ctx->have_traj = true;
+    return MPC_OK;
+}
+
+extern "C" int mpc_set_guidance(mpc_ctx *ctx, const double *ref_xy, int M, const mpc_goal *goals, int ngoals,
+                                const double *goal_segs, int nseg, double b) {
+    if (!ctx || !ctx->stream) return MPC_E_STATE;
+    if (M < 0 || ngoals < 0 || nseg < 0 || (M > 0 && !ref_xy) || (ngoals > 0 && !goals) || (nseg > 0 && !goal_segs))
+        return fail(ctx, MPC_E_ARG, "bad guidance arguments");
+    for (int g = 0; g < ngoals; g++)
+        if (goals[g].seg_begin >= 0 && (goals[g].seg_end < goals[g].seg_begin || goals[g].seg_end > nseg))
+            return fail(ctx, MPC_E_ARG, "goal %d: segment range %d..%d outside 0..%d", g, goals[g].seg_begin, goals[g].seg_end, nseg);
+    CU(cudaSetDevice(ctx->device));
+    ctx->have_guidance = false;
+    static_assert(sizeof(mpc_goal) == sizeof(EGoal), "goal record layout");
+    CU(ensure(ctx, ctx->g_ref, sizeof(double) * 2 * (size_t)std::max(M, 1)));
+    CU(ensure(ctx, ctx->g_goals, sizeof(EGoal) * (size_t)std::max(ngoals, 1)));
+    CU(ensure(ctx, ctx->g_segs, sizeof(double) * 4 * (size_t)std::max(nseg, 1)));
+    if (M) CU(cudaMemcpyAsync(ctx->g_ref.p, ref_xy, sizeof(double) * 2 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+    if (ngoals) CU(cudaMemcpyAsync(ctx->g_goals.p, goals, sizeof(EGoal) * (size_t)ngoals, cudaMemcpyHostToDevice, ctx->stream));
+    if (nseg) CU(cudaMemcpyAsync(ctx->g_segs.p, goal_segs, sizeof(double) * 4 * (size_t)nseg, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->g_M = M; ctx->g_ngoals = ngoals; ctx->g_nseg = nseg; ctx->g_b = b;
+    ctx->have_guidance = true;
+    return MPC_OK;
+}
+
+extern "C" int mpc_expand(mpc_ctx *ctx, int B, const mpc_query_desc *queries, const int32_t *cand_idx, int ncand,
+                          const double *parent, unsigned mode, uint32_t *out_mask, int mask_words, double *out_cost,
+                          int32_t *out_goal_step, mpc_stats *stats) {
+    if (!ctx || !ctx->stream) return MPC_E_STATE;
+    if (!ctx->have_traj || !ctx->have_guidance) return fail(ctx, MPC_E_STATE, "upload the trajectories and the guidance before expanding");
+    int rc = prepare_host(ctx, B, queries, cand_idx, ncand, mode, false);      // validates the batch, packs the collision part
+    if (rc) return rc;
+    if (ctx->tr_P != ctx->P) return fail(ctx, MPC_E_STATE, "trajectories for %d primitives, library has %d", ctx->tr_P, ctx->P);
+    long long total = 0;
+    for (int q = 0; q < B; q++) total += queries[q].cand_cnt;
+    if (total > 0x7fffffffLL) return fail(ctx, MPC_E_LIMIT, "batch too large");
+    if (total > 0 && (!parent || !out_cost || !out_goal_step)) return fail(ctx, MPC_E_ARG, "parent / out_cost / out_goal_step missing");
+    if (total > 0) {
+        // pack: EQuery[B] | out_off[B+1] | explicit candidates; results: cost[total] | goal_step[total]
+        const size_t b_q = sizeof(EQuery) * (size_t)B, b_o = (sizeof(int) * (size_t)(B + 1) + 15) / 16 * 16, b_c = sizeof(int) * (size_t)ncand;
+        const size_t b_in = b_q + b_o + b_c, b_cost = sizeof(double) * (size_t)total, b_out = b_cost + sizeof(int) * (size_t)total;
+        if (b_in + b_out > ctx->h_exp_cap) {
+            if (ctx->h_exp) cudaFreeHost(ctx->h_exp);
+            ctx->h_exp = nullptr;
+            ctx->h_exp_cap = 0;
+            CU(cudaMallocHost(&ctx->h_exp, (b_in + b_out) * 2));
+            ctx->h_exp_cap = (b_in + b_out) * 2;
+        }
+        CU(ensure(ctx, ctx->e_pack, b_in));
+        CU(ensure(ctx, ctx->e_out, b_out));
+        EQuery *hq = (EQuery *)ctx->h_exp;
+        int *hoff = (int *)((char *)ctx->h_exp + b_q);
+        int acc = 0;
+        for (int q = 0; q < B; q++) {
+            const mpc_query_desc &d = queries[q];
+            EQuery &o = hq[q];
+            o.x = d.x; o.y = d.y; o.c = d.c; o.s = d.s;
+            o.cost = parent[2 * q]; o.phi = parent[2 * q + 1];
+            o.t0 = d.t0;
+            o.cand_src = d.cand_set < 0;
+            o.cand_base = d.cand_set < 0 ? d.cand_off : ctx->set_off[d.cand_set] + d.cand_off;
+            o.cand_cnt = d.cand_cnt;
+            hoff[q] = acc;
+            acc += d.cand_cnt;
+        }
+        hoff[B] = acc;
+        if (ncand) memcpy((char *)ctx->h_exp + b_q + b_o, cand_idx, b_c);
+        cudaStream_t st = ctx->stream;
+        CU(cudaMemcpyAsync(ctx->e_pack.p, ctx->h_exp, b_in, cudaMemcpyHostToDevice, st));
+        EParams e;
+        e.q = (const EQuery *)ctx->e_pack.p;
+        e.out_off = (const int *)((const char *)ctx->e_pack.p + b_q);
+        e.B = B; e.total = (int)total;
+        e.sets = (const int *)ctx->sets.p;
+        e.explicit_cand = (const int *)((const char *)ctx->e_pack.p + b_q + b_o);
+        e.states = (const double *)ctx->tr_states.p; e.nstates = (const int *)ctx->tr_n.p; e.L = ctx->tr_L;
+        e.ref_xy = (const double *)ctx->g_ref.p; e.M = ctx->g_M;
+        e.goals = (const EGoal *)ctx->g_goals.p; e.ngoals = ctx->g_ngoals;
+        e.goal_segs = (const double *)ctx->g_segs.p; e.b = ctx->g_b;
+        e.cost = (double *)ctx->e_out.p;
+        e.goal_step = (int *)((char *)ctx->e_out.p + b_cost);
+        k_expand<<<(int)((total + 127) / 128), 128, 0, st>>>(e);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync((char *)ctx->h_exp + b_in, ctx->e_out.p, b_out, cudaMemcpyDeviceToHost, st));
+        rc = run_batch(ctx, out_mask, mask_words, stats);          // same stream; its synchronisation covers the copy above
+        if (rc) return rc;
+        memcpy(out_cost, (const char *)ctx->h_exp + b_in, b_cost);
+        memcpy(out_goal_step, (const char *)ctx->h_exp + b_in + b_cost, sizeof(int) * (size_t)total);
+        if (stats) stats->kernels += 1;
+        return MPC_OK;
+    }
+    return run_batch(ctx, out_mask, mask_words, stats);
 }

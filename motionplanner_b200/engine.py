@@ -171,6 +171,40 @@ class CollisionEngine:
         mask, st = self.query_mask(queries, cand_idx, mode)
         return unpack_mask(mask, queries), st
 
+    # -- primitive-selection step ---------------------------------------------------------------------
+    def upload_trajectories(self, states, nstates):
+        """states [P, L, 4] = primitive.x transposed, nstates [P] = primitive.x.shape[1]; once per automaton"""
+        states = _arr(states, np.float64)
+        nstates = _arr(nstates, np.int32)
+        assert states.ndim == 3 and states.shape[2] == 4 and nstates.shape == (states.shape[0],)
+        self._check(self._L.mpc_upload_trajectories(self._ctx, _cabi.ptr(states), _cabi.ptr(nstates), states.shape[0],
+                                                    states.shape[1]), "mpc_upload_trajectories")
+
+    def set_guidance(self, ref_xy, goals, goal_segs, b):
+        """ref_xy [2, M] = ref_traj[0:2]; goals: GOAL_DTYPE records; goal_segs [n, 4]; b = param['b']"""
+        ref_xy = _arr(ref_xy, np.float64)
+        goals = _arr(goals, _cabi.GOAL_DTYPE)
+        goal_segs = _arr(goal_segs if goal_segs is not None else np.zeros((0, 4)), np.float64).reshape(-1, 4)
+        assert ref_xy.ndim == 2 and ref_xy.shape[0] == 2
+        self._check(self._L.mpc_set_guidance(self._ctx, _cabi.ptr(ref_xy), ref_xy.shape[1], _cabi.ptr(goals), len(goals),
+                                             _cabi.ptr(goal_segs), len(goal_segs), float(b)), "mpc_set_guidance")
+
+    def expand(self, queries, parent, cand_idx=None, mode=MODE_PLANNER):
+        """collision bits + child cost + goal step of every candidate: (uint8 [n], float64 [n], int32 [n], stats)"""
+        queries = _arr(queries, QUERY_DTYPE)
+        cand = _arr(cand_idx, np.int32) if cand_idx is not None else np.zeros(0, np.int32)
+        parent = _arr(parent, np.float64).reshape(len(queries), 2)
+        nw = mask_words(queries)
+        n = int(queries['cand_cnt'].sum())
+        mask = np.zeros(max(nw, 1), dtype=np.uint32)
+        cost = np.zeros(max(n, 1))
+        goal = np.zeros(max(n, 1), np.int32)
+        st = _cabi.Stats()
+        self._check(self._L.mpc_expand(self._ctx, len(queries), _cabi.ptr(queries), _cabi.ptr(cand), len(cand),
+                                       _cabi.ptr(parent), int(mode), _cabi.ptr(mask), nw, _cabi.ptr(cost),
+                                       _cabi.ptr(goal), C.byref(st)), "mpc_expand")
+        return unpack_mask(mask[:nw], queries), cost[:n], goal[:n], st.as_dict()
+
     # -- measurement (bench.py) ------------------------------------------------------------------------------------
     def prepare(self, queries, cand_idx=None, mode=MODE_PLANNER):
         queries = _arr(queries, QUERY_DTYPE)

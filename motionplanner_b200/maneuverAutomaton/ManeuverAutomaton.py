@@ -84,6 +84,18 @@ class ManeuverAutomaton:
         probe = self.primitives[1] if len(self.primitives) > 1 else self.primitives[0]
         return 'starttime' not in probe.occ[0]
 
+    def trajectory_layout(self):
+        """(states [P, L, 4], nstates [P]) for mpc_upload_trajectories: primitive.x transposed, padded to the longest"""
+        if getattr(self, '_traj_layout', None) is None:
+            L = max(p.x.shape[1] for p in self.primitives)
+            states = np.zeros((len(self.primitives), L, 4))
+            nstates = np.zeros(len(self.primitives), np.int32)
+            for i, p in enumerate(self.primitives):
+                states[i, :p.x.shape[1]] = p.x.T
+                nstates[i] = p.x.shape[1]
+            self._traj_layout = (states, nstates)
+        return self._traj_layout
+
     def device_layout(self, time_step):
         """flat arrays for mpc_upload_library.
 

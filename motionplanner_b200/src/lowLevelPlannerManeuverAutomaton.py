@@ -13,6 +13,8 @@ What changed is *when* the geometry is evaluated: when a node is expanded, all i
 60-195 primitives x <= 11 occupancies) are decided by a single mpc_query and each child carries its bit; popping a
 child then only applies the time guard of the reference (:99-109) and reads the bit.
 """
+import operator
+
 import numpy as np
 import scipy.linalg
 
@@ -21,24 +23,32 @@ from ..geometry import Point
 from ..maneuverAutomaton.Controller import FeedbackController
 
 
+_COST = operator.attrgetter('cost')      # stable sort key of the search queue (reference :54)
+
+
 class Node:
     """search node: sequence of primitive indices, rear-axle trajectory 4 x (10 k + 1), accumulated cost.
     Children created by the batched expansion keep (parent, own segment) and build ``x`` on first use -- only nodes
     that are actually popped ever need the full trajectory."""
-    __slots__ = ('primitives', '_x', 'cost', 'collides', '_parent', '_seg')
+    __slots__ = ('primitives', '_x', 'cost', 'collides', '_parent', '_seg', 'goal_step')
 
-    def __init__(self, primitives, x, cost, collides=None, parent=None, seg=None):
+    def __init__(self, primitives, x, cost, collides=None, parent=None, seg=None, goal_step=None):
         self.primitives = primitives
         self._x = x
         self.cost = cost
         self.collides = collides          # geometry bit of the last primitive (None: not evaluated yet)
         self._parent, self._seg = parent, seg
+        self.goal_step = goal_step        # device-side goal test: step index, -1 = not reached, None = not evaluated
 
     @property
     def x(self):
         if self._x is None:
-            self._x = np.concatenate((self._parent.x[:, :-1], self._seg), axis=1)
-            self._parent = None
+            seg = self._seg
+            if not isinstance(seg, np.ndarray):        # device expansion: `seg` is the primitive, transform on first use
+                px = self._parent.x
+                seg = _rotation(px[3, -1]) @ seg.x + np.array([[px[0, -1]], [px[1, -1]], [0], [px[3, -1]]])
+            self._x = np.concatenate((self._parent.x[:, :-1], seg), axis=1)
+            self._parent = self._seg = None
         return self._x
 
     @x.setter
@@ -109,6 +119,8 @@ def _checker_for(MA, time_step, space, timepoint, backend=None):
 
 def goal_check(node, primitive, param):
     """first step of the last primitive whose vehicle centre lies in a goal set inside its time window (:127-142)"""
+    if getattr(node, 'goal_step', None) is not None:          # decided on the device together with the collision bits
+        return (True, int(node.goal_step)) if node.goal_step >= 0 else (False, None)
     ind = node.x.shape[1] - primitive.x.shape[1]
     for i in range(ind, node.x.shape[1]):
         for goal in param['goal']:
@@ -143,6 +155,17 @@ def _children(checker, node, MA, bucket, ref_traj, fixed, param, scenes):
     cand = MA.vel_dic[bucket]
     if not cand:
         return []
+    depth = len(node.primitives) + 1
+    if getattr(checker, 'device_expand', False):
+        # bits, costs and goal steps of all children from one mpc_expand call; trajectories are built when popped
+        bits, costs, goal = checker.bucket_expand(x[0, -1], x[1, -1], x[3, -1], node.cost, ind, param['steps'], bucket, scenes)
+        if _time_exceeded(ind, param['goal']):
+            bits = np.ones(len(cand), bool)
+        prims = MA.primitives
+        fix = fixed[depth - 1] if depth <= len(fixed) else None
+        base = node.primitives
+        return [Node(base + [i], None, (c + 1000 if fix is not None and i != fix else c), b, node, prims[i], g)
+                for i, c, b, g in zip(cand, costs.tolist(), bits.tolist(), goal.tolist())]
     if _time_exceeded(ind, param['goal']):
         bits = np.ones(len(cand), bool)           # the reference rejects these before looking at geometry (:99-109)
     else:
@@ -164,7 +187,6 @@ def _children(checker, node, MA, bucket, ref_traj, fixed, param, scenes):
             costs[loc] = node.cost + 0.0
         for k, i in enumerate(loc):
             segs[i] = X[k]
-    depth = len(node.primitives) + 1
     out = []
     for k, i in enumerate(cand):
         cost = costs[k]
@@ -175,10 +197,16 @@ def _children(checker, node, MA, bucket, ref_traj, fixed, param, scenes):
 
 
 def lowLevelPlannerManeuverAutomaton(scenario, planning_problem, param, space_all, ref_traj, MA, search_horizon=2,
-                                     backend=None):
-    """plan a concrete trajectory for the given high-level plan using a maneuver automaton"""
+                                     backend=None, device_expand=False):
+    """plan a concrete trajectory for the given high-level plan using a maneuver automaton.
+
+    device_expand=True moves the rest of the primitive-selection step to the GPU as well (mpc_expand: child costs and
+    goal tests next to the collision bits); the default keeps them in numpy."""
     timepoint = MA.is_timepoint()
     checker = _checker_for(MA, param['time_step'], space_all, timepoint, backend)
+    checker.device_expand = bool(device_expand)
+    if device_expand:
+        checker.enable_expand(ref_traj, param['goal'], param['b'])
     scenes = (0,) if timepoint else (0, 1)
     param['_MA'] = MA
 
@@ -192,7 +220,7 @@ def lowLevelPlannerManeuverAutomaton(scenario, planning_problem, param, space_al
     queue = _children(checker, node, MA, int(MA._bucket(param['v_init'])), ref_traj, fixed, param, scenes)
 
     while len(queue) > 0:
-        queue.sort(key=lambda n: n.cost)
+        queue.sort(key=_COST)
         node = queue.pop(0)
         primitive = MA.primitives[node.primitives[-1]]
 

@@ -11,6 +11,8 @@ boundary as segments plus the obstacle pieces of every step -- which is what the
 """
 from copy import deepcopy
 
+import operator
+
 import numpy as np
 
 from ..auxiliary.polygonLaneletNetwork import polygonLaneletNetwork
@@ -18,6 +20,9 @@ from ..checker import PrimitiveChecker, SceneSet, scenario_obstacle_arrays
 from ..geometry import Point
 from ..maneuverAutomaton.Controller import FeedbackController
 from .lowLevelPlannerManeuverAutomaton import (Node, _rotation, extract_control_inputs, transform_trajectory)
+
+
+_COST = operator.attrgetter('cost')      # stable sort key of the search queue (reference :54)
 
 
 class FreeSpace:
@@ -197,7 +202,7 @@ def maneuverAutomatonPlannerStandalone(scenario, planning_problem, param, MA, ba
     queue = _children(checker, node, MA, int(MA._bucket(x0[2])), goal_set, param)
     popped = 0
     while len(queue) > 0:
-        queue.sort(key=lambda n: n.cost)
+        queue.sort(key=_COST)
         node = queue.pop(0)
         popped += 1
         if max_nodes is not None and popped > max_nodes:

@@ -64,6 +64,10 @@ def lib():
             f.argtypes = [C.POINTER(OrcProblem), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                           C.POINTER(OrcStats), C.c_int]
             f.restype = C.c_int
+        L.orc_expand.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                 C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]
+        L.orc_expand.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -140,3 +144,28 @@ class Problem:
         assert rc == 0
         return out, dict(pairs_decided=st.pairs_decided, pairs_nominal=st.pairs_nominal,
                          near_tangent=st.near_tangent, exact_calls=st.exact_calls)
+
+
+GOAL_DTYPE = np.dtype([("time_start", "<i4"), ("time_end", "<i4"), ("seg_begin", "<i4"), ("seg_end", "<i4")])
+
+
+def expand(states, nstates, ref_xy, goals, goal_segs, b, set_off, set_idx, queries, cand_idx, parent):
+    """cost and goal-hit step of every child (orc_expand): returns (cost float64 [n], goal_step int32 [n], -1 = none)"""
+    states = np.ascontiguousarray(states, np.float64)
+    nstates = np.ascontiguousarray(nstates, np.int32)
+    ref_xy = np.ascontiguousarray(ref_xy, np.float64)
+    goals = np.ascontiguousarray(goals, GOAL_DTYPE)
+    goal_segs = np.ascontiguousarray(goal_segs if goal_segs is not None else np.zeros((0, 4)), np.float64)
+    set_off = np.ascontiguousarray(set_off, np.int32)
+    set_idx = np.ascontiguousarray(set_idx, np.int32)
+    queries = np.ascontiguousarray(queries, QUERY_DTYPE)
+    cand = np.ascontiguousarray(cand_idx, np.int32) if cand_idx is not None else np.zeros(0, np.int32)
+    parent = np.ascontiguousarray(parent, np.float64).reshape(len(queries), 2)
+    n = int(queries["cand_cnt"].sum())
+    cost = np.zeros(n)
+    goal = np.zeros(n, np.int32)
+    rc = lib().orc_expand(_p(states), _p(nstates), states.shape[0], states.shape[1], _p(ref_xy), ref_xy.shape[1],
+                          _p(goals), len(goals), _p(goal_segs), float(b), _p(set_off), _p(set_idx), _p(queries),
+                          len(queries), _p(cand), _p(parent), _p(cost), _p(goal))
+    assert rc == 0, rc
+    return cost, goal

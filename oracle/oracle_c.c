@@ -422,3 +422,95 @@ int orc_check_batch_inner(const orc_problem_t *pb, const orc_query_t *queries, i
     if (stats) *stats = total;
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* primitive-selection step: cost and goal test of every child of an expansion                       */
+/* ------------------------------------------------------------------------------------------------------------------ */
+
+typedef struct {
+    int32_t time_start, time_end; /* goal['time_start'] <= i <= goal['time_end']   (reference :136)                     */
+    int32_t seg_begin, seg_end;   /* boundary segments of goal['space'] in goal_segs; seg_begin < 0: space is None      */
+} orc_goal_t;
+
+/* numpy's pairwise summation of a contiguous float64 run (numpy/_core/src/umath/loops_utils.h.src, n <= 128), the
+ * routine np.sum runs over `(ref_traj[0:2, index] - x[0:2, index])**2` (reference :210): eight running sums, combined
+ * as a tree, then the tail in order */
+static double numpy_pairwise_sum(const double *a, int n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; i++) res += a[i];
+        return res;
+    }
+    double r[8];
+    for (int j = 0; j < 8; j++) r[j] = a[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; j++) r[j] += a[i + j];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; i++) res += a[i];
+    return res;
+}
+
+#define ORC_MAX_STATES 64
+
+/* For every candidate (flat order over the queries): the cost expand_node gives the child (reference :199-210, without
+ * the +1000 fixed-prefix penalty of :212, which is search bookkeeping) and the index goal_check returns for it
+ * (reference :127-142), -1 when no goal set is reached.
+ *   states [P][L][4]  primitive.x transposed (x, y, v, phi per step, rear-axle frame), nstates[P] = primitive.x.shape[1]
+ *   ref_xy [2][M]     ref_traj[0:2]
+ *   parent [B][2]     node.cost, node.x[3, -1]; the query's (x, y, c, s) are node.x[0:2, -1], cos, sin; t0 = ind
+ * The elements are summed in the order numpy visits them: the fancy-indexed operands are Fortran-ordered, i.e.
+ * x0, y0, x1, y1, ... */
+int orc_expand(const double *states, const int32_t *nstates, int P, int L, const double *ref_xy, int M,
+               const orc_goal_t *goals, int ngoals, const double *goal_segs, double b, const int32_t *set_off,
+               const int32_t *set_idx, const orc_query_t *queries, int B, const int32_t *cand_idx, const double *parent,
+               double *out_cost, int32_t *out_goal) {
+    long long base = 0;
+    if (L > ORC_MAX_STATES) return -1;
+    for (int q = 0; q < B; q++) {
+        const orc_query_t *qq = &queries[q];
+        const int32_t *list = (qq->cand_set >= 0) ? set_idx + set_off[qq->cand_set] + qq->cand_off : cand_idx + qq->cand_off;
+        const double pcost = parent[2 * q], pphi = parent[2 * q + 1];
+        const int ind = qq->t0;
+        for (int i = 0; i < qq->cand_cnt; i++) {
+            const int p = list[i];
+            if (p < 0 || p >= P) return -2;
+            const int n = nstates[p];
+            const double *st = states + (size_t)p * L * 4;
+            double X[ORC_MAX_STATES], Y[ORC_MAX_STATES], a[2 * ORC_MAX_STATES];
+            /* x_ = T @ primitive.x + [x, y, 0, phi]   (reference :199).  numpy hands the 4x4 @ 4xL product to its BLAS,
+             * whose kernels accumulate with fused multiply-adds along k: c*x first, then fma(-s, y, .); the zero
+             * entries of T add nothing.  (Checked against numpy in tests/test_expand_cpu.py; the float tolerance for
+             * a BLAS that rounds differently is 1e-12 relative, stated there.) */
+            for (int k = 0; k < n; k++) {
+                X[k] = fma(-qq->s, st[4 * k + 1], qq->c * st[4 * k]) + qq->x;
+                Y[k] = fma(qq->c, st[4 * k + 1], qq->s * st[4 * k]) + qq->y;
+            }
+            int K = n < M - ind ? n : M - ind;     /* index = range(ind, min(x.shape[1], ref_traj.shape[1])) (:204-207) */
+            if (K < 0) K = 0;
+            for (int k = 0; k < K; k++) {
+                double dx = ref_xy[ind + k] - X[k], dy = ref_xy[(size_t)M + ind + k] - Y[k];
+                a[2 * k] = dx * dx;
+                a[2 * k + 1] = dy * dy;
+            }
+            out_cost[base + i] = pcost + numpy_pairwise_sum(a, 2 * K);
+            int hit = -1;
+            for (int k = 0; k < n && hit < 0; k++) {
+                const int step = ind + k;
+                for (int g = 0; g < ngoals; g++) {
+                    if (!(goals[g].time_start <= step && step <= goals[g].time_end)) continue;
+                    const double th = st[4 * k + 3] + pphi;
+                    const double px = X[k] + cos(th) * b, py = Y[k] + sin(th) * b;
+                    if (goals[g].seg_begin < 0 ||
+                        point_in_soup(px, py, goal_segs + 4 * (size_t)goals[g].seg_begin, goals[g].seg_end - goals[g].seg_begin) == 1) {
+                        hit = step;
+                        break;
+                    }
+                }
+            }
+            out_goal[base + i] = hit;
+        }
+        base += qq->cand_cnt;
+    }
+    return 0;
+}

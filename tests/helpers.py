@@ -43,6 +43,21 @@ class OracleBackend:
         return bits, st
 
 
+    # primitive-selection step (mpc_expand stand-in)
+    def upload_trajectories(self, states, nstates):
+        self.traj = (np.array(states, np.float64), np.array(nstates, np.int32))
+
+    def set_guidance(self, ref_xy, goals, goal_segs, b):
+        self.guidance = (np.array(ref_xy, np.float64), np.array(goals), np.array(goal_segs, np.float64).reshape(-1, 4), float(b))
+
+    def expand(self, queries, parent, cand_idx=None, mode=0):
+        bits, st = self.query(queries, cand_idx, mode)
+        ref, goals, segs, b = self.guidance
+        cost, goal = orc.expand(self.traj[0], self.traj[1], ref, goals, segs, b, self.lib['set_off'], self.lib['set_idx'],
+                                queries, cand_idx, parent)
+        return bits, cost, goal, st
+
+
 def load_golden():
     z = np.load(GOLDEN)
     out = {}

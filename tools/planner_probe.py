@@ -21,7 +21,8 @@ from motionplanner_b200.src import lowLevelPlannerManeuverAutomaton as LL  # noq
 def main():
     MA = load_maneuver_automaton()
     MA.device_layout(0.1)
-    for name, make in (("gpu", lambda: CollisionEngine(0)), ("cpu-oracle", OracleBackend)):
+    for name, make, dev in (("gpu", lambda: CollisionEngine(0), False), ("gpu+expand", lambda: CollisionEngine(0), True),
+                            ("cpu-oracle", OracleBackend, False)):
         be = make()
         times, nq = [], 0
         for rep in range(12):
@@ -30,7 +31,7 @@ def main():
             t0 = time.perf_counter()
             chk = LL._checker_for(MA, 0.1, space, True, be)          # stages library + free space
             t1 = time.perf_counter()
-            x, u, _ = LL.lowLevelPlannerManeuverAutomaton(None, None, param, space, ref, MA, backend=be)
+            x, u, _ = LL.lowLevelPlannerManeuverAutomaton(None, None, param, space, ref, MA, backend=be, device_expand=dev)
             t2 = time.perf_counter()
             times.append((t1 - t0, t2 - t1))
             nq = chk.stats['queries']
