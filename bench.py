@@ -171,7 +171,8 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--queries", type=int, default=16, help="queries (ego poses) per step")
+    ap.add_argument("--queries", type=int, default=64,
+                    help="queries (ego poses) per step; default = the 64 jittered poses SURVEY.md 8(d) defines for C4")
     ap.add_argument("--ref-queries", type=int, default=2, help="queries per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -304,6 +305,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
             "config": {"workload": "C4 dense traffic: 4096 primitives x 256 obstacles x 50 timesteps per query "
                                    "(BASELINE.json configs[3])", "queries_per_step": nq,
+                       "queries_what": "one step = one batch of ego poses (seed 2 jitter) against one staged scene",
                        "checks_per_step": checks_step, "seeds": [0, 1, 2], "l2": "flushed before every timed step "
                        "(256 MiB fill)", "early_exit": "warp-wide per tile", "parallelism": "replicated library, "
                        "queries sharded per GPU, no collective on the hot path"},

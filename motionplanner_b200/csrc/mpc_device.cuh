@@ -42,7 +42,7 @@ struct KParams {
     int PJ, J, lib_vmax;
     // scenes
     const float4 *ob_f;          // [F-1][ob_stride] vertex and edge-line fields, slot layout (steps 32-aligned)
-    const float4 *ob_box;        // [ob_stride/32] bounding box of the circles of every block of 32 slots
+    const float4 *ob_box;        // [ob_stride/8] bounding box of the circles of every sub-block of 8 slots
     const float *ob_c;           // [3][ob_stride]   bounding circle x | y | r, slot layout
     const double *ob_v64;
     const int *ob_nv;
@@ -54,7 +54,7 @@ struct KParams {
     const float *maxabs_scene;
     // queries
     const QDev *q;
-    const int *cta_off, *cand, *cand_pos;
+    const int *cta_off, *cand, *cand_pos, *cand_inv;      // cand_pos: sorted -> caller's position in the set, cand_inv: back
     int B, nwords;
     unsigned *mask;              // result bits, caller's candidate order
     unsigned *mask_sorted;       // result bits of spatially sorted candidate sets, un-permuted by k_refine
@@ -305,12 +305,16 @@ __global__ void k_stage_obst(int nslots, const double *__restrict__ src64, const
     ob_c[slot] = ccx;
     ob_c[(size_t)stride + slot] = ccy;
     ob_c[(size_t)2 * stride + slot] = ccr;
-    // bounding box of the block's circles (of the float32 values the main kernel will see)
+    // bounding box of the circles of every sub-block of 8 slots (of the float32 values the main kernel will see)
     const bool real = nv > 0;
-    const float x0 = warp_min(real ? ccx - ccr : BIG), x1 = warp_max(real ? ccx + ccr : -BIG);
-    const float y0 = warp_min(real ? ccy - ccr : BIG), y1 = warp_max(real ? ccy + ccr : -BIG);
-    if ((threadIdx.x & 31) == 0)
-        ob_box[slot >> 5] = make_float4(__fadd_rd(x0, -1e-6f * fabsf(x0)), __fadd_rd(y0, -1e-6f * fabsf(y0)),
+    float x0 = real ? ccx - ccr : BIG, x1 = real ? ccx + ccr : -BIG, y0 = real ? ccy - ccr : BIG, y1 = real ? ccy + ccr : -BIG;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        x0 = fminf(x0, __shfl_xor_sync(FULL, x0, d)); x1 = fmaxf(x1, __shfl_xor_sync(FULL, x1, d));
+        y0 = fminf(y0, __shfl_xor_sync(FULL, y0, d)); y1 = fmaxf(y1, __shfl_xor_sync(FULL, y1, d));
+    }
+    if ((threadIdx.x & 7) == 0)
+        ob_box[slot >> 3] = make_float4(__fadd_rd(x0, -1e-6f * fabsf(x0)), __fadd_rd(y0, -1e-6f * fabsf(y0)),
                                         __fadd_ru(x1, 1e-6f * fabsf(x1)), __fadd_ru(y1, 1e-6f * fabsf(y1)));
 }
 
@@ -441,10 +445,13 @@ __device__ __forceinline__ float sat_segment(const PolyRegs<VA> &A, const float4
 }
 
 constexpr int K_THREADS = 256;      // 8 warps share one staged tile
+#ifndef K_MIN_CTAS
+#define K_MIN_CTAS 4
+#endif
 constexpr int QCAP = 64;            // per-warp queue of (lane, record) pairs that passed axis 0
 
 template <int VA, int VB, bool COUNT, bool NOCULL>
-__global__ void __launch_bounds__(K_THREADS, 4) k_check(const KParams p) {
+__global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p) {
     constexpr int F = ob_fields(VB), FA = ob_fields(VA), NW = K_THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_raw);
@@ -697,42 +704,55 @@ __global__ void __launch_bounds__(K_THREADS, 4) k_check(const KParams p) {
                 const float4 *s_cy4 = reinterpret_cast<const float4 *>(s_c + p.cap_o);
                 const float4 *s_cr4 = reinterpret_cast<const float4 *>(s_c + 2 * p.cap_o);
                 const f32x2 nax = pack2(-acx, -acx), nay = pack2(-acy, -acy);
-                // which blocks of 32 slots can matter: lane b tests block b (one load latency for the whole tile).  A
-                // block whose circles (box already inflated by their radii) cannot come within rcull of any centre of
-                // this warp has every pair separated on the box axis.
-                unsigned live_o = FULL;
+                // which sub-blocks of 8 slots can matter: lane b tests sub-blocks b and b + 32 (one load latency for the
+                // whole tile).  A sub-block whose circles (box already inflated by their radii) cannot come within
+                // rcull of any centre of this warp has every pair separated on the box axis.
+                unsigned long long live_o = ~0ull;
                 if (cull_o) {
-                    const int nblk = ocn >> 5;               // <= 10 (cap_o <= 320)
-                    bool live = false;
-                    if (lane < nblk) {
-                        const float4 bb = __ldg(p.ob_box + ((o0 + oc0) >> 5) + lane);
-                        live = !(bb.x > wx1 + rcull || bb.z < wx0 - rcull || bb.y > wy1 + rcull || bb.w < wy0 - rcull);
+                    const int nsb = ocn >> 3;                // <= 40 (cap_o <= 320)
+                    const float4 *bx = p.ob_box + ((o0 + oc0) >> 3);
+                    bool l0 = false, l1 = false;
+                    if (lane < nsb) {
+                        const float4 bb = __ldg(bx + lane);
+                        l0 = !(bb.x > wx1 + rcull || bb.z < wx0 - rcull || bb.y > wy1 + rcull || bb.w < wy0 - rcull);
                     }
-                    live_o = __ballot_sync(FULL, live);
+                    if (lane + 32 < nsb) {
+                        const float4 bb = __ldg(bx + lane + 32);
+                        l1 = !(bb.x > wx1 + rcull || bb.z < wx0 - rcull || bb.y > wy1 + rcull || bb.w < wy0 - rcull);
+                    }
+                    live_o = (unsigned long long)__ballot_sync(FULL, l0) | ((unsigned long long)__ballot_sync(FULL, l1) << 32);
                 }
                 for (int ob = 0; ob < ocn; ob += 32) {
-                    if (!((live_o >> (ob >> 5)) & 1u)) {
-                        if (COUNT && active) n_skip += min(32, nobst - oc0 - ob);
-                        continue;
+                    const unsigned m4 = (unsigned)(live_o >> (ob >> 3)) & 0xFu;
+                    if (COUNT && active) {
+#pragma unroll
+                        for (int sub = 0; sub < 4; sub++) {
+                            const int real = max(0, min(8, nobst - oc0 - ob - 8 * sub));
+                            if ((m4 >> sub) & 1u) n_cull += real; else n_skip += real;
+                        }
                     }
+                    if (!m4) continue;
                     // axis 0: centre line with bounding radii.  Three warp-broadcast LDS.128 bring four obstacles; packed
                     // FADD2/FFMA2 evaluate e = |dc|^2 - (rb + rcull)^2 for two of them per instruction and the sign bit
                     // of e is shifted into the hit word (bit 31-k <-> slot ob+k).
                     unsigned hits = 0;
 #pragma unroll
-                    for (int qd = 0; qd < 8; qd++) {
-                        const float4 X = s_cx4[(ob >> 2) + qd], Y = s_cy4[(ob >> 2) + qd], R = s_cr4[(ob >> 2) + qd];
-                        const f32x2 dx01 = add2(pack2(X.x, X.y), nax), dy01 = add2(pack2(Y.x, Y.y), nay);
-                        const f32x2 dx23 = add2(pack2(X.z, X.w), nax), dy23 = add2(pack2(Y.z, Y.w), nay);
-                        const f32x2 e01 = fma2(dx01, dx01, fma2(dy01, dy01, pack2(R.x, R.y)));
-                        const f32x2 e23 = fma2(dx23, dx23, fma2(dy23, dy23, pack2(R.z, R.w)));
-                        hits = __funnelshift_l((unsigned)e01, hits, 1);
-                        hits = __funnelshift_l((unsigned)(e01 >> 32), hits, 1);
-                        hits = __funnelshift_l((unsigned)e23, hits, 1);
-                        hits = __funnelshift_l((unsigned)(e23 >> 32), hits, 1);
+                    for (int sub = 0; sub < 4; sub++) {
+                        if (!((m4 >> sub) & 1u)) { hits <<= 8; continue; }
+#pragma unroll
+                        for (int qd = 2 * sub; qd < 2 * sub + 2; qd++) {
+                            const float4 X = s_cx4[(ob >> 2) + qd], Y = s_cy4[(ob >> 2) + qd], R = s_cr4[(ob >> 2) + qd];
+                            const f32x2 dx01 = add2(pack2(X.x, X.y), nax), dy01 = add2(pack2(Y.x, Y.y), nay);
+                            const f32x2 dx23 = add2(pack2(X.z, X.w), nax), dy23 = add2(pack2(Y.z, Y.w), nay);
+                            const f32x2 e01 = fma2(dx01, dx01, fma2(dy01, dy01, pack2(R.x, R.y)));
+                            const f32x2 e23 = fma2(dx23, dx23, fma2(dy23, dy23, pack2(R.z, R.w)));
+                            hits = __funnelshift_l((unsigned)e01, hits, 1);
+                            hits = __funnelshift_l((unsigned)(e01 >> 32), hits, 1);
+                            hits = __funnelshift_l((unsigned)e23, hits, 1);
+                            hits = __funnelshift_l((unsigned)(e23 >> 32), hits, 1);
+                        }
                     }
                     if (!active || (collide && !noexit)) hits = 0;
-                    if (COUNT && active) n_cull += min(32, nobst - oc0 - ob);
                     push_hits(hits, ob, drain_obst);
                     if (qn >= 32) {
                         drain_obst();
@@ -856,7 +876,7 @@ __global__ void __launch_bounds__(K_THREADS, 4) k_check(const KParams p) {
 // so the lanes split them and votes put the answer together.  A single thread needs ~20 k cycles per polygon pair
 // (dependent float64 chains, local-memory polygon arrays); a warp needs ~1-2 k, which is what a planner that waits on
 // every query cares about.
-__global__ void __launch_bounds__(128) k_refine(const KParams p) {
+__global__ void __launch_bounds__(128, 8) k_refine(const KParams p) {
     __shared__ double s_pts[4][2 * (MPC_MAX_LIB_VERTS + MPC_MAX_OBST_VERTS)];
     const unsigned n = min(p.cnt->wl_count, (unsigned)p.wl_cap);
     const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -864,25 +884,26 @@ __global__ void __launch_bounds__(128) k_refine(const KParams p) {
     double *Ax = s_pts[wib], *Ay = Ax + MPC_MAX_LIB_VERTS, *Bx = Ay + MPC_MAX_LIB_VERTS, *By = Bx + MPC_MAX_OBST_VERTS;
     unsigned refined = 0, ties = 0, near_t = 0, par_ref = 0;
     const bool strict = p.mode & MPC_MODE_VALIDATOR;
-    // phase A: result bits of spatially sorted candidate sets go home to the caller's candidate order: one thread per
-    // mask word (its query found by bisection on the mask offsets), only set bits cost an atomic
-    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < p.nwords; w += gridDim.x * blockDim.x) {
-        unsigned bits = p.mask_sorted[w];
-        if (!bits) continue;
+    // phase A: result bits of spatially sorted candidate sets go home to the caller's candidate order.  One warp per
+    // destination mask word: lane = candidate, which looks up its position in the sorted set and fetches its bit (a
+    // gather: no atomics, no serial chain per word); one OR per word merges with the bits phase B adds below.
+    for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < (unsigned)p.nwords; w += warps) {
         int lo = 0, hi = p.B;
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
-            if (p.q[mid].mask_off <= w) lo = mid; else hi = mid;
+            if (p.q[mid].mask_off <= (int)w) lo = mid; else hi = mid;
         }
-        while (lo + 1 < p.B && p.q[lo + 1].mask_off <= w) lo++;          // queries without candidates share an offset
+        while (lo + 1 < p.B && p.q[lo + 1].mask_off <= (int)w) lo++;     // queries without candidates share an offset
         const QDev *Q = p.q + lo;
-        const int base = Q->pos_base + (w - Q->mask_off) * 32;
-        while (bits) {
-            const int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const int oi = __ldg(p.cand_pos + base + b);
-            atomicOr(p.mask + Q->mask_off + (oi >> 5), 1u << (oi & 31));
+        if (Q->pos_base < 0) continue;                                    // caller's order already
+        const int ci = ((int)w - Q->mask_off) * 32 + (int)lane;
+        bool bit = false;
+        if (ci < Q->cand_cnt) {
+            const int sp = __ldg(p.cand_inv + Q->pos_base + ci);          // position of candidate ci in the sorted set
+            bit = (p.mask_sorted[Q->mask_off + (sp >> 5)] >> (sp & 31)) & 1u;
         }
+        const unsigned word = __ballot_sync(FULL, bit);
+        if (lane == 0 && word) atomicOr(p.mask + w, word);
     }
     for (unsigned item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n; item += warps) {
         const int4 e = p.wl[item];
@@ -931,22 +952,26 @@ __global__ void __launch_bounds__(128) k_refine(const KParams p) {
             }
             const bool sepA = (~badA & ((1u << nA) - 1u)) != 0, sepB = (~badB & ((1u << nB) - 1u)) != 0;
             collide = !(sepA || sepB);
-            // near-tangent statistic: |separation| < 1e-9 m, one edge per lane
-            double mine = -1e300;
+            // near-tangent statistic: |separation| < 1e-9 m with separation = max over edges of (min signed distance of
+            // the other polygon's vertices).  One edge per lane, compared in squared form (no sqrt, no division):
+            //   s_e < +eps  <=>  mn_e < 0  or  mn_e^2 < eps^2 |e|^2 ;   s_e > -eps  <=>  mn_e > 0  or  mn_e^2 < eps^2 |e|^2
+            bool below = true, above = false;      // all edges below +eps / some edge above -eps
             if ((int)lane < nA + nB) {
                 const bool fromA = (int)lane < nA;
                 const int ee = fromA ? lane : lane - nA, nn = fromA ? nA : nB, e1 = (ee + 1 == nn) ? 0 : ee + 1;
                 const double *Px = fromA ? Ax : Bx, *Py = fromA ? Ay : By, *Qx = fromA ? Bx : Ax, *Qy = fromA ? By : Ay;
                 const int nq = fromA ? nB : nA;
-                const double ex = Px[e1] - Px[ee], ey = Py[e1] - Py[ee], len = sqrt(ex * ex + ey * ey);
-                if (len > 0.0) {
+                const double ex = Px[e1] - Px[ee], ey = Py[e1] - Py[ee], len2 = ex * ex + ey * ey;
+                if (len2 > 0.0) {
                     double mn = 1e300;
                     for (int k = 0; k < nq; k++) mn = fmin(mn, ey * (Qx[k] - Px[ee]) - ex * (Qy[k] - Py[ee]));
-                    mine = mn / len;
+                    const bool tiny = mn * mn < 1e-18 * len2;
+                    below = mn < 0.0 || tiny;
+                    above = mn > 0.0 || tiny;
                 }
             }
-            for (int o = 16; o; o >>= 1) mine = fmax(mine, __shfl_xor_sync(FULL, mine, o));
-            if (lane == 0) { if (fabs(mine) < 1e-9) near_t++; refined++; }
+            const bool near = __all_sync(FULL, below) && __any_sync(FULL, above);
+            if (lane == 0) { if (near) near_t++; refined++; }
         } else if (kind == KIND_SEG) {
             __syncwarp();
             const double *sg = p.sg_64 + 4 * (size_t)obj;

@@ -366,7 +366,7 @@ extern "C" int mpc_upload_library(mpc_ctx *ctx, const double *verts, const int32
         // primitives' last occupancy centre (whole-set queries): neighbouring lanes then hold neighbouring polygons at
         // every time step, which is what makes the per-warp block culling of k_check selective.  pos[] maps a sorted
         // entry back to its slot in the caller's order (that is where its result bit goes).
-        std::vector<int> both((size_t)2 * std::max(total, 1)), pos((size_t)std::max(total, 1));
+        std::vector<int> both((size_t)2 * std::max(total, 1)), pos((size_t)2 * std::max(total, 1));     // pos: [sorted -> caller's position | inverse]
         for (int i = 0; i < total; i++) both[i] = set_idx[i];
         for (int sidx = 0; sidx < nsets; sidx++) {
             const int b = set_off[sidx], e = set_off[sidx + 1], n = e - b;
@@ -388,6 +388,7 @@ extern "C" int mpc_upload_library(mpc_ctx *ctx, const double *verts, const int32
             for (int i = 0; i < n; i++) {
                 both[(size_t)total + b + i] = set_idx[b + order[i].second];
                 pos[b + i] = order[i].second;
+                pos[(size_t)total + b + order[i].second] = i;
             }
         }
         // the library once more, in sorted-set order and slot-major, for coalesced reads by k_check
@@ -413,7 +414,7 @@ extern "C" int mpc_upload_library(mpc_ctx *ctx, const double *verts, const int32
             CU(cudaMemcpyAsync(ctx->slib_n.p, sn.data(), sn.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
             CU(cudaMemcpyAsync(ctx->slib_c.p, scv.data(), scv.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
             CU(cudaMemcpyAsync(ctx->sets.p, both.data(), (size_t)2 * total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-            CU(cudaMemcpyAsync(ctx->sets_pos.p, pos.data(), (size_t)total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->sets_pos.p, pos.data(), (size_t)2 * total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
         }
     }
@@ -504,7 +505,7 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     CU(ensure(ctx, ctx->ob_nv, (size_t)ob_stride * sizeof(int)));
     CU(ensure(ctx, ctx->ob_f, (size_t)ob_stride * F * sizeof(float4)));
     CU(ensure(ctx, ctx->ob_c, (size_t)ob_stride * 3 * sizeof(float)));
-    CU(ensure(ctx, ctx->ob_box, (size_t)(ob_stride / 32 + 1) * sizeof(float4)));
+    CU(ensure(ctx, ctx->ob_box, (size_t)(ob_stride / 8 + 1) * sizeof(float4)));
     CU(ensure(ctx, ctx->ob_order, (size_t)ob_stride * sizeof(int)));
     CU(ensure(ctx, ctx->sg_f, (size_t)sg_stride * 2 * sizeof(float4)));
     CU(ensure(ctx, ctx->sg_box, (size_t)(sg_stride / 32 + 1) * sizeof(float4)));
@@ -648,6 +649,7 @@ static KParams make_params(mpc_ctx *ctx) {
     char *qp = (char *)ctx->qpack_d.p;
     p.q = (const QDev *)qp; p.cta_off = (const int *)(qp + ctx->qpack_cta_off); p.cand = (const int *)ctx->cand_d.p;
     p.cand_pos = (const int *)ctx->sets_pos.p;
+    p.cand_inv = p.cand_pos + ctx->set_total;
     p.B = ctx->B;
     p.cnt = (Counters *)ctx->res_d.p; p.mask = (unsigned *)((char *)ctx->res_d.p + sizeof(Counters));
     p.mask_sorted = p.mask + ctx->mask_words;
