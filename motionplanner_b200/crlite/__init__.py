@@ -166,6 +166,17 @@ class Lanelet:
         self.adj_left = self.adj_right = None
         self.adj_left_same_direction = self.adj_right_same_direction = None
         self.polygon = Polygon(np.concatenate([right, np.flip(left, 0)]))
+        # commonroad Lanelet.distance: arc length of the centre line up to every centre vertex
+        self.distance = np.concatenate([[0.0], np.cumsum(np.linalg.norm(np.diff(self.center_vertices, axis=0), axis=1))])
+
+    def orientation_by_position(self, position):
+        """direction of the centre-line segment closest to `position` (commonroad Lanelet.orientation_by_position)"""
+        c = self.center_vertices
+        a, d = c[:-1], c[1:] - c[:-1]
+        n2 = np.maximum((d * d).sum(axis=1), 1e-300)
+        t = np.clip(((np.asarray(position) - a) * d).sum(axis=1) / n2, 0.0, 1.0)
+        k = int(np.argmin(np.linalg.norm(a + t[:, None] * d - np.asarray(position), axis=1)))
+        return float(np.arctan2(d[k, 1], d[k, 0]))
 
 
 class LaneletNetwork:
@@ -179,6 +190,19 @@ class LaneletNetwork:
     def find_lanelet_by_position(self, points):
         return [[l.lanelet_id for l in self.lanelets if l.polygon.contains_point(p)] for p in points]
 
+    def find_most_likely_lanelet_by_state(self, state_list):
+        """per state the lanelet that contains its position and whose direction there is closest to the state's
+        orientation (commonroad LaneletNetwork.find_most_likely_lanelet_by_state); states off the road give nothing"""
+        out = []
+        for st in state_list:
+            ids = self.find_lanelet_by_position([st.position])[0]
+            if not ids:
+                continue
+            diff = [abs(make_valid_orientation(self._by_id[i].orientation_by_position(st.position) - st.orientation))
+                    for i in ids]
+            out.append(ids[int(np.argmin(diff))])
+        return out
+
 
 class Scenario:
     def __init__(self, dt, scenario_id, lanelet_network, static_obstacles, dynamic_obstacles, tags):
@@ -188,6 +212,21 @@ class Scenario:
     @property
     def obstacles(self):
         return list(self.static_obstacles) + list(self.dynamic_obstacles)
+
+    # the part of commonroad's Scenario editing interface auxiliary/prediction.py uses (:41-42, :166-172)
+    def remove_obstacle(self, obstacle):
+        for lst in (self.static_obstacles, self.dynamic_obstacles):
+            if obstacle in lst:
+                lst.remove(obstacle)
+
+    def add_objects(self, obj):
+        for o in (obj if isinstance(obj, (list, tuple)) else [obj]):
+            (self.static_obstacles if o.obstacle_role == 'static' else self.dynamic_obstacles).append(o)
+
+    def generate_object_id(self):
+        ids = [o.obstacle_id for o in self.obstacles] + [l.lanelet_id for l in self.lanelet_network.lanelets]
+        self._next_id = max([getattr(self, '_next_id', 0)] + ids) + 1
+        return self._next_id
 
 
 class GoalRegion:
