@@ -346,8 +346,12 @@ __global__ void k_stage_segs(int nslots, const double *__restrict__ sg64, const 
     }
     float x0 = valid ? fminf(rec.x, rec.z) : BIG, x1 = valid ? fmaxf(rec.x, rec.z) : -BIG;
     float y0 = valid ? fminf(rec.y, rec.w) : BIG, y1 = valid ? fmaxf(rec.y, rec.w) : -BIG;
-    x0 = warp_min(x0); y0 = warp_min(y0); x1 = warp_max(x1); y1 = warp_max(y1);
-    if ((threadIdx.x & 31) == 0 && s < nslots) sg_box[s >> 5] = make_float4(x0, y0, x1, y1);
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {            // one box per sub-block of 8 slots
+        x0 = fminf(x0, __shfl_xor_sync(FULL, x0, d)); x1 = fmaxf(x1, __shfl_xor_sync(FULL, x1, d));
+        y0 = fminf(y0, __shfl_xor_sync(FULL, y0, d)); y1 = fmaxf(y1, __shfl_xor_sync(FULL, y1, d));
+    }
+    if ((threadIdx.x & 7) == 0 && s < nslots) sg_box[s >> 3] = make_float4(x0, y0, x1, y1);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -450,7 +454,11 @@ constexpr int K_THREADS = 256;      // 8 warps share one staged tile
 #endif
 constexpr int QCAP = 64;            // per-warp queue of (lane, record) pairs that passed axis 0
 
-template <int VA, int VB, bool COUNT, bool NOCULL>
+// SEGCULL: a step may have more than one block of 32 boundary segments, compile the sub-block culling of segments in.
+// The kernel is sensitive to its shape: with that code present C4 (4 segments per step) runs 5 % slower; the same
+// switch for obstacles changes nothing, and funnelling the three inlined copies of each drain into one call site
+// (smaller code, more control flow per round) costs 8-15 %.
+template <int VA, int VB, bool COUNT, bool NOCULL, bool SEGCULL>
 __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p) {
     constexpr int F = ob_fields(VB), FA = ob_fields(VA), NW = K_THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -606,7 +614,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
             unsigned qn = 0;                        // entries in this warp's queue (warp-uniform)
             // bounding box of the warp's 32 polygon centres: decides which 32-blocks of the spatially sorted obstacle
             // slots / boundary segments can matter for anyone in the warp
-            const bool cull_o = !NOCULL && nslot > 32, cull_s = !NOCULL && nseg > 32;
+            const bool cull_o = !NOCULL && nslot > 32, cull_s = SEGCULL && !NOCULL && nseg > 32;
             float wx0 = 0.f, wx1 = 0.f, wy0 = 0.f, wy1 = 0.f, wr = 0.f;
             if (cull_o || cull_s) {
                 wx0 = warp_min(active ? acx : BIG); wx1 = warp_max(active ? acx : -BIG);
@@ -765,16 +773,16 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
             // ---- boundary segments of the free space at this time step -----------------------------------------
             if (scn && (noexit || !__all_sync(FULL, collide || !active))) {
                 const bool blockcull = cull_s;        // a single block cannot be skipped: no box work
-                const float4 *boxes = p.sg_box + ((g0 + sc0) >> 5);
+                const float4 *boxes = p.sg_box + ((g0 + sc0) >> 3);      // one box per sub-block of 8 segment slots
                 // the even-odd ray may run along +x, -x, +y or -y; take the direction whose ray corridor meets the
-                // fewest blocks of the whole range (a road aligned with the ray would otherwise keep every block alive)
+                // fewest sub-blocks of the whole range (a road aligned with the ray would otherwise keep all of them)
                 int dir = 0;
                 if (blockcull) {
-                    const float4 *all = p.sg_box + (g0 >> 5);
-                    const int nblk = (nseg + 31) >> 5;
+                    const float4 *all = p.sg_box + (g0 >> 3);
+                    const int nsb = (nseg + 7) >> 3;
                     int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-                    for (int b = lane; b < ((nblk + 31) & ~31); b += 32) {
-                        float4 bb = (b < nblk) ? __ldg(all + b) : make_float4(BIG, BIG, -BIG, -BIG);
+                    for (int b = lane; b < ((nsb + 31) & ~31); b += 32) {
+                        float4 bb = (b < nsb) ? __ldg(all + b) : make_float4(BIG, BIG, -BIG, -BIG);
                         const bool iny = bb.w >= wy0 && bb.y <= wy1, inx = bb.z >= wx0 && bb.x <= wx1;
                         c0 += __popc(__ballot_sync(FULL, iny && bb.z >= wx0));      // +x
                         c1 += __popc(__ballot_sync(FULL, iny && bb.x <= wx1));      // -x
@@ -788,45 +796,65 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
                 }
                 const bool ray_y = dir >= 2, flip = (dir == 1) || (dir == 2);
                 const float pc = ray_y ? acx : acy;          // coordinate the ray keeps constant
-                // live blocks of this phase (<= 16: cap_s <= 512), lane b tests block b
-                unsigned live_s = FULL;
+                // live sub-blocks of this phase (<= 64: cap_s <= 512), lane b tests sub-blocks b and b + 32
+                unsigned long long live_s = ~0ull;
                 if (blockcull) {
-                    bool live = false;
-                    if (lane < ((scn + 31) >> 5)) {
-                        const float4 bb = __ldg(boxes + lane);
+                    const int nsb = (scn + 7) >> 3;
+                    auto test = [&](int b) -> bool {
+                        if (b >= nsb) return false;
+                        const float4 bb = __ldg(boxes + b);
                         // a segment can meet a polygon only if the boxes overlap; it can be crossed by the ray of a
                         // centre only if it reaches that centre's constant coordinate and is not entirely behind it
                         const bool sat_rel = bb.x <= wx1 + wr && bb.z >= wx0 - wr && bb.y <= wy1 + wr && bb.w >= wy0 - wr;
                         const bool iny = bb.w >= wy0 && bb.y <= wy1, inx = bb.z >= wx0 && bb.x <= wx1;
                         const bool par_rel = dir == 0 ? (iny && bb.z >= wx0) : dir == 1 ? (iny && bb.x <= wx1)
                                            : dir == 2 ? (inx && bb.w >= wy0) : (inx && bb.y <= wy1);
-                        live = sat_rel || par_rel;
-                    }
-                    live_s = __ballot_sync(FULL, live);
+                        return sat_rel || par_rel;
+                    };
+                    const bool l0 = test(lane), l1 = test(lane + 32);
+                    live_s = (unsigned long long)__ballot_sync(FULL, l0) | ((unsigned long long)__ballot_sync(FULL, l1) << 32);
                 }
+                // one segment against the lane's polygon centre: crossing parity of the centre's ray + "near" test
+                auto seg_one = [&](int idx, int k, unsigned &hits) {
+                    float4 sa = s_sg[idx], sl = s_sg[p.cap_s + idx];
+                    float dl = fmaf(sl.x, acx, fmaf(sl.y, acy, -sl.z));       // centre to the segment's line
+                    // even-odd crossing parity of the ray from the polygon centre.  The two comparisons are exact on
+                    // the float32 data and consistent between segments that share a vertex; the side test is trusted
+                    // only outside the error band
+                    const float ea = ray_y ? sa.x : sa.y, eb = ray_y ? sa.z : sa.w;
+                    bool ua = ea > pc, ub = eb > pc;
+                    if (ua != ub) {
+                        par ^= (ub != flip) ? (dl < 0.f) : (dl > 0.f);
+                        punc |= fabsf(dl) <= tau;
+                    }
+                    float tt = fmaf(-sl.y, acx - 0.5f * (sa.x + sa.z), sl.x * (acy - 0.5f * (sa.y + sa.w)));
+                    bool near = NOCULL ? (sl.w >= 0.f) : ((fabsf(dl) <= arr) & (fabsf(tt) <= sl.w + arr));
+                    if (near) hits |= 0x80000000u >> k;
+                };
                 for (int sb = 0; sb < scn; sb += 32) {
                     const int cnt = min(32, scn - sb);
-                    if (!((live_s >> (sb >> 5)) & 1u)) continue;
                     unsigned hits = 0;
+                    if (!blockcull) {
 #pragma unroll 2
-                    for (int k = 0; k < cnt; k++) {
-                        float4 sa = s_sg[sb + k], sl = s_sg[p.cap_s + sb + k];
-                        float dl = fmaf(sl.x, acx, fmaf(sl.y, acy, -sl.z));       // centre to the segment's line
-                        // even-odd crossing parity of the ray from the polygon centre.  The two comparisons are exact
-                        // on the float32 data and consistent between segments that share a vertex; the side test is
-                        // trusted only outside the error band
-                        const float ea = ray_y ? sa.x : sa.y, eb = ray_y ? sa.z : sa.w;
-                        bool ua = ea > pc, ub = eb > pc;
-                        if (ua != ub) {
-                            par ^= (ub != flip) ? (dl < 0.f) : (dl > 0.f);
-                            punc |= fabsf(dl) <= tau;
+                        for (int k = 0; k < cnt; k++) seg_one(sb + k, k, hits);
+                        if (COUNT && active) n_cull += cnt;
+                    } else {
+                        const unsigned m4 = (unsigned)(live_s >> (sb >> 3)) & 0xFu;
+                        if (COUNT && active) {
+                            for (int sub = 0; sub < 4; sub++) {
+                                const int real = max(0, min(8, cnt - 8 * sub));
+                                if ((m4 >> sub) & 1u) n_cull += real; else n_skip += real;
+                            }
                         }
-                        float tt = fmaf(-sl.y, acx - 0.5f * (sa.x + sa.z), sl.x * (acy - 0.5f * (sa.y + sa.w)));
-                        bool near = NOCULL ? (sl.w >= 0.f) : ((fabsf(dl) <= arr) & (fabsf(tt) <= sl.w + arr));
-                        if (near) hits |= 0x80000000u >> k;
+                        if (!m4) continue;
+                        for (int sub = 0; sub < 4 && 8 * sub < cnt; sub++) {
+                            if (!((m4 >> sub) & 1u)) continue;
+                            const int kend = min(8 * sub + 8, cnt);
+#pragma unroll 2
+                            for (int k = 8 * sub; k < kend; k++) seg_one(sb + k, k, hits);
+                        }
                     }
                     if (!active || (collide && !noexit)) hits = 0;
-                    if (COUNT && active) n_cull += cnt;
                     push_hits(hits, sb, drain_seg);
                     if (qn >= 32) drain_seg();
                 }

@@ -508,7 +508,7 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     CU(ensure(ctx, ctx->ob_box, (size_t)(ob_stride / 8 + 1) * sizeof(float4)));
     CU(ensure(ctx, ctx->ob_order, (size_t)ob_stride * sizeof(int)));
     CU(ensure(ctx, ctx->sg_f, (size_t)sg_stride * 2 * sizeof(float4)));
-    CU(ensure(ctx, ctx->sg_box, (size_t)(sg_stride / 32 + 1) * sizeof(float4)));
+    CU(ensure(ctx, ctx->sg_box, (size_t)(sg_stride / 8 + 1) * sizeof(float4)));
     lap("validate + ensure");
     cudaStream_t st = ctx->stream;
     // the small per-scene arrays travel as one packed block (one driver call instead of nine)
@@ -660,12 +660,13 @@ static KParams make_params(mpc_ctx *ctx) {
     return p;
 }
 
-template <int VA, int VB>
+template <int VA, int VB, bool SEGCULL>
 static cudaError_t launch_check_vb(mpc_ctx *ctx, const KParams &p) {
     const bool count = ctx->mode & MPC_MODE_COUNT_WORK, nocull = ctx->mode & MPC_MODE_NO_CULL;
-    auto kern = nocull ? (count ? k_check<VA, VB, true, true> : k_check<VA, VB, false, true>)
-                       : (count ? k_check<VA, VB, true, false> : k_check<VA, VB, false, false>);
-    const int key = VA * 1000 + VB * 10 + (count ? 1 : 0) + (nocull ? 2 : 0);
+    // full evaluation never culls: one instantiation per (COUNT) is enough
+    auto kern = nocull ? (count ? k_check<VA, VB, true, true, false> : k_check<VA, VB, false, true, false>)
+                       : (count ? k_check<VA, VB, true, false, SEGCULL> : k_check<VA, VB, false, false, SEGCULL>);
+    const int key = VA * 1000 + VB * 10 + (count ? 1 : 0) + (nocull ? 2 : (SEGCULL ? 4 : 0));
     if (ctx->smem > 48 * 1024 && ctx->smem_attr[key] < ctx->smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem);
         if (e != cudaSuccess) return e;
@@ -675,15 +676,22 @@ static cudaError_t launch_check_vb(mpc_ctx *ctx, const KParams &p) {
     return cudaGetLastError();
 }
 
+template <int VA, int VB>
+static cudaError_t launch_check_seg(mpc_ctx *ctx, const KParams &p) {
+    // steps with more than one block of 32 boundary segments get the instantiation with the segment sub-block culling
+    // compiled in (the kernel is sensitive to its code size: C4, 4 segments, runs 5 % slower with it)
+    return ctx->max_seg_step > 32 ? launch_check_vb<VA, VB, true>(ctx, p) : launch_check_vb<VA, VB, false>(ctx, p);
+}
+
 static cudaError_t launch_check(mpc_ctx *ctx, const KParams &p) {
     if (ctx->ctas == 0) return cudaSuccess;
     const int va = ctx->VA, vb = ctx->VB;
-    if (va == 4 && vb == 4) return launch_check_vb<4, 4>(ctx, p);
-    if (va == 4 && vb == 8) return launch_check_vb<4, 8>(ctx, p);
-    if (va == 8 && vb == 4) return launch_check_vb<8, 4>(ctx, p);
-    if (va == 8 && vb == 8) return launch_check_vb<8, 8>(ctx, p);
-    if (va == 16 && vb == 4) return launch_check_vb<16, 4>(ctx, p);
-    return launch_check_vb<16, 8>(ctx, p);
+    if (va == 4 && vb == 4) return launch_check_seg<4, 4>(ctx, p);
+    if (va == 4 && vb == 8) return launch_check_seg<4, 8>(ctx, p);
+    if (va == 8 && vb == 4) return launch_check_seg<8, 4>(ctx, p);
+    if (va == 8 && vb == 8) return launch_check_seg<8, 8>(ctx, p);
+    if (va == 16 && vb == 4) return launch_check_seg<16, 4>(ctx, p);
+    return launch_check_seg<16, 8>(ctx, p);
 }
 
 static int launch_all(mpc_ctx *ctx, cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2) {
