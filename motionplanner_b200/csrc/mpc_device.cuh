@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(256) k_order_obst(const double *__restrict__ s
     __shared__ int s_idx[SORT_MAX];
     const int step = blockIdx.x;
     const int o0 = src_off[step], cnt = src_off[step + 1] - o0, s0 = slot_off[step], nslot = slot_off[step + 1] - s0;
-    if (cnt > SORT_MAX) {
+    // a single block of 32 slots is never culled by boxes: its order does not matter
+    if (cnt > SORT_MAX || cnt <= 32) {
         for (int i = threadIdx.x; i < nslot; i += blockDim.x) order[s0 + i] = (i < cnt) ? o0 + i : -1;
         return;
     }

@@ -427,10 +427,24 @@ extern "C" int mpc_upload_library(mpc_ctx *ctx, const double *verts, const int32
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+static int set_scenes_impl(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_off, const double *origins,
+                           const int32_t *step_obst_off, const double *obst, const int32_t *obst_nv, int Vo,
+                           const int32_t *step_seg_begin, const int32_t *step_seg_end, const double *segs, int nseg);
+
 extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_off, const double *origins,
                               const int32_t *step_obst_off, const double *obst, const int32_t *obst_nv, int Vo,
                               const int32_t *step_seg_begin, const int32_t *step_seg_end, const double *segs, int nseg) {
     if (!ctx || !ctx->stream) return MPC_E_STATE;
+    const int rc = set_scenes_impl(ctx, nscenes, scene_step_off, origins, step_obst_off, obst, obst_nv, Vo, step_seg_begin,
+                                   step_seg_end, segs, nseg);
+    // the obstacle copy is started before the host-side passes: never hand the caller's buffers back with it in flight
+    if (rc != MPC_OK) cudaStreamSynchronize(ctx->stream);
+    return rc;
+}
+
+static int set_scenes_impl(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_off, const double *origins,
+                           const int32_t *step_obst_off, const double *obst, const int32_t *obst_nv, int Vo,
+                           const int32_t *step_seg_begin, const int32_t *step_seg_end, const double *segs, int nseg) {
     if (nscenes <= 0 || !scene_step_off || !origins || !step_obst_off || !step_seg_begin || !step_seg_end)
         return fail(ctx, MPC_E_ARG, "bad scene arguments");
     CU(cudaSetDevice(ctx->device));
@@ -446,6 +460,16 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     if (nobst > 0 && (!obst || !obst_nv)) return fail(ctx, MPC_E_ARG, "obstacle arrays missing");
     if (nobst > 0 && (Vo < 3 || Vo > MPC_MAX_OBST_VERTS)) return fail(ctx, MPC_E_LIMIT, "Vo=%d outside 3..%d", Vo, MPC_MAX_OBST_VERTS);
     if (nseg > 0 && !segs) return fail(ctx, MPC_E_ARG, "segment array missing");
+    cudaStream_t st = ctx->stream;
+    // the bulk of the bytes first: the caller's obstacle rows travel as they are (one contiguous DMA, read by the staging
+    // kernels with stride Vo) while the host validates and sorts the rest
+    CU(ensure(ctx, ctx->ob_src, (size_t)std::max(nobst, 1) * Vo * 2 * sizeof(double)));
+    CU(ensure(ctx, ctx->ob_src_nv, (size_t)std::max(nobst, 1) * sizeof(int)));
+    if (nobst) {
+        CU(cudaMemcpyAsync(ctx->ob_src.p, obst, (size_t)nobst * Vo * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->ob_src_nv.p, obst_nv, (size_t)nobst * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    lap("start obstacle copy");
 
     // ---- boundary segments: every distinct [begin, end) range becomes a 32-aligned, spatially sorted (Morton order of
     // the midpoints) block range on the device, so that k_check can skip whole blocks by their bounding box
@@ -484,11 +508,13 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     }
     lap("pass 1 (ranges)");
     const int nslots = nslots_acc;
-    int vmax_used = 3;
+    int vmax_used = 3, vmin_used = 0;
+#pragma omp parallel for reduction(max : vmax_used) reduction(min : vmin_used) if (nobst > 65536)
     for (int o = 0; o < nobst; o++) {
-        if (obst_nv[o] > Vo || obst_nv[o] < 0) return fail(ctx, MPC_E_ARG, "obst_nv[%d]=%d outside 0..%d", o, obst_nv[o], Vo);
         vmax_used = std::max(vmax_used, (int)obst_nv[o]);
+        vmin_used = std::min(vmin_used, (int)obst_nv[o]);
     }
+    if (vmax_used > Vo || vmin_used < 0) return fail(ctx, MPC_E_ARG, "obst_nv outside 0..%d (min %d, max %d)", Vo, vmin_used, vmax_used);
     const int VB = vmax_used <= 4 ? 4 : 8;
     const int F = ob_fields(VB);
     // obstacle slots: the obstacles of step k live in the 32-aligned range [slot_off[k], slot_off[k+1])
@@ -499,8 +525,6 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     }
     const int noslots = slot_off[nsteps];
     const int ob_stride = std::max(noslots, 32), sg_stride = std::max(nslots, 32);
-    CU(ensure(ctx, ctx->ob_src, (size_t)std::max(nobst, 1) * Vo * 2 * sizeof(double)));
-    CU(ensure(ctx, ctx->ob_src_nv, (size_t)std::max(nobst, 1) * sizeof(int)));
     CU(ensure(ctx, ctx->ob_in, (size_t)ob_stride * VB * 2 * sizeof(double)));
     CU(ensure(ctx, ctx->ob_nv, (size_t)ob_stride * sizeof(int)));
     CU(ensure(ctx, ctx->ob_f, (size_t)ob_stride * F * sizeof(float4)));
@@ -510,7 +534,6 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     CU(ensure(ctx, ctx->sg_f, (size_t)sg_stride * 2 * sizeof(float4)));
     CU(ensure(ctx, ctx->sg_box, (size_t)(sg_stride / 8 + 1) * sizeof(float4)));
     lap("validate + ensure");
-    cudaStream_t st = ctx->stream;
     // the small per-scene arrays travel as one packed block (one driver call instead of nine)
     {
         const size_t n_org = (size_t)nscenes * 2 * sizeof(double), n_sg = (size_t)sg_stride * 4 * sizeof(double);
@@ -581,9 +604,6 @@ extern "C" int mpc_set_scenes(mpc_ctx *ctx, int nscenes, const int32_t *scene_st
     }
     CU(cudaMemsetAsync(ctx->maxabs.p, 0, sizeof(float), st));
     if (nobst) {
-        // the caller's rows travel as they are (one contiguous DMA); the staging kernels read them with stride Vo
-        CU(cudaMemcpyAsync(ctx->ob_src.p, obst, (size_t)nobst * Vo * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(ctx->ob_src_nv.p, obst_nv, (size_t)nobst * sizeof(int), cudaMemcpyHostToDevice, st));
         int blocks = (noslots + 127) / 128;
         if (VB == 4) {
             k_order_obst<4><<<nsteps, 256, 0, st>>>((const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_src_off.p,
