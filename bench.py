@@ -40,8 +40,8 @@ FLOP_PER_CHECK = 304            # rectangle x rectangle SAT, a =
 SAT_FLOP_EXECUTED = 160         # this kernel's full 4x4 test: 64 FMA (2 flop) + 24 min + 8 max
 CULL_FLOP_EXECUTED = 6          # centre-line axis per pair: 2 add + 2 fma (packed FADD2/FFMA2: two pairs per instruction)
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # no FP32 entry in MEASURED_PEAKS.json: derived from its sm_max_mhz
-NCU_DRAM_BYTES_PER_LAUNCH = 17679872   # ncu capture g (profiles/): dram__bytes_read.sum of one 64-query launch; write 0
-NCU_WARP_INST_PER_LAUNCH = 550727389   # same capture: smsp__inst_executed.sum of that launch (a count, not a time)
+NCU_DRAM_BYTES_PER_LAUNCH = 17681152   # ncu capture h (profiles/): dram__bytes_read.sum of one 64-query launch; write 0
+NCU_WARP_INST_PER_LAUNCH = 545235312   # same capture: smsp__inst_executed.sum of that launch (a count, not a time)
 ISSUE_PEAK = 148 * 4 * 1.965e9         # warp instructions per second: 4 schedulers per SM, one issue per clock
 METRIC = "primitive x obstacle x timestep collision checks/sec"
 
@@ -320,14 +320,14 @@ def main():
             "gpu_launches_what": "per timed step: k_fill_u32 (L2 flush, outside the event bracket), k_check, k_refine",
             "clocks": clocks,
             "roofline": {
-                "bound": "fp32", "kernel": "k_check<4,4,0,0>", "achieved": exec_tflops, "peak": FP32_PEAK_TFLOPS,
+                "bound": "fp32", "kernel": "k_check<4,4,0,0,0>", "achieved": exec_tflops, "peak": FP32_PEAK_TFLOPS,
                 "unit": "TFLOP/s", "frac": exec_tflops / FP32_PEAK_TFLOPS,
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH if nq == 64 else None,
                 "what": "executed FP32 flop of the timed launch (an instrumented launch of the same batch counts "
                         "centre-line axis tests x 6 flop and full separating-axis tests x 160 flop) / CUDA-event "
-                        "duration of k_check. The kernel is NOT FP32-bound: ncu (profiles/r01g_k_check_ncu_full.csv) "
-                        "shows instruction issue at 80 % of peak (see issue_slots), ALU pipe 57 %, FMA pipe 24 %, "
-                        "shared-memory data pipe 52 %; sub-block bounding boxes separate 87 % of the pairs wholesale, "
+                        "duration of k_check. The kernel is NOT FP32-bound: ncu (profiles/r01h_k_check_ncu_full.csv) "
+                        "shows instruction issue at 81 % of peak (see issue_slots), ALU pipe 57 %, FMA pipe 24 %, "
+                        "shared-memory data pipe 54 %; sub-block bounding boxes separate 87 % of the pairs wholesale, "
                         "the centre-line axis (6 flop) all but 0.4 % of the rest; HBM traffic equals the algorithmic "
                         "bytes.",
                 "peak_source": "derived: 148 SM x 128 lanes x 2 x sm_max_mhz 1965 (MEASURED_PEAKS.json has no FP32 "
@@ -353,9 +353,9 @@ def main():
                                 "note": "the binding resource per ncu: executed warp instructions of one launch (count "
                                         "from the committed capture) / live CUDA-event duration, against 148 SM x 4 "
                                         "schedulers x sm_max_mhz"},
-                "ncu": {"source": "profiles/r01g_k_check_ncu_full.csv", "smsp__issue_active_pct": 80.3,
-                        "l1tex__data_pipe_lsu_wavefronts_pct": 51.8, "sm__inst_executed_pipe_fma_pct": 23.7,
-                        "sm__inst_executed_pipe_alu_pct": 57.3, "smsp__inst_executed": NCU_WARP_INST_PER_LAUNCH,
+                "ncu": {"source": "profiles/r01h_k_check_ncu_full.csv", "smsp__issue_active_pct": 80.8,
+                        "l1tex__data_pipe_lsu_wavefronts_pct": 54.2, "sm__inst_executed_pipe_fma_pct": 23.9,
+                        "sm__inst_executed_pipe_alu_pct": 57.0, "smsp__inst_executed": NCU_WARP_INST_PER_LAUNCH,
                         "dram__bytes_read": NCU_DRAM_BYTES_PER_LAUNCH, "dram__bytes_write": 0},
                 "hbm": {"algorithmic_bytes": algo_bytes, "achieved_gbs": algo_bytes / (main_ms * 1e-3) / 1e9,
                         "peak_gbs": hbm_peak, "frac": algo_bytes / (main_ms * 1e-3) / 1e9 / hbm_peak,
