@@ -44,6 +44,7 @@ NCU_DRAM_BYTES_PER_LAUNCH = 17681152   # ncu capture h (profiles/): dram__bytes_
 NCU_WARP_INST_PER_LAUNCH = 545235312   # same capture: smsp__inst_executed.sum of that launch (a count, not a time)
 ISSUE_PEAK = 148 * 4 * 1.965e9         # warp instructions per second: 4 schedulers per SM, one issue per clock
 METRIC = "primitive x obstacle x timestep collision checks/sec"
+WORKLOAD = ("C4 dense traffic: 4096 primitives x 256 obstacles x 50 timesteps per query (BASELINE.json configs[3])")
 
 
 def measured_peaks():
@@ -155,11 +156,12 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "checks/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C4 dense traffic 4096 primitives x 256 obstacles x 50 timesteps per query",
-                       "queries_per_step": len(queries), "seeds": [0, 1, 2]},
+            "config": {"workload": WORKLOAD, "queries_per_step": args.queries, "seeds": [0, 1, 2],
+                       "sample_queries_per_step": len(queries)},
             "cpu_baseline": {"value": v, "unit": "checks/s", "cores": cores, "kind": "port",
-                             "sample": "each step = %d C4 queries through oracle/oracle_c.c (float64, exact signs, "
-                                       "reference early return), OpenMP %d threads" % (len(queries), cores)},
+                             "sample": "each step = %d of the %d C4 queries of a step through oracle/oracle_c.c (float64, "
+                                       "exact signs, reference early return), OpenMP %d threads"
+                                       % (len(queries), args.queries, cores)},
             "e2e": {"value": v, "unit": "checks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "shapely/commonroad-io are not installable offline, so the reference's CPU path is timed through "
@@ -305,8 +307,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "checks/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-            "config": {"workload": "C4 dense traffic: 4096 primitives x 256 obstacles x 50 timesteps per query "
-                                   "(BASELINE.json configs[3])", "queries_per_step": nq,
+            "config": {"workload": WORKLOAD, "queries_per_step": nq,
                        "queries_what": "one step = one batch of ego poses (seed 2 jitter) against one staged scene",
                        "checks_per_step": checks_step, "seeds": [0, 1, 2], "l2": "flushed before every timed step "
                        "(256 MiB fill)", "early_exit": "warp-wide per tile", "parallelism": "replicated library, "
