@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MPC_ABI_VERSION 1
+#define MPC_ABI_VERSION 2
 
 /* error codes */
 #define MPC_OK 0
@@ -74,6 +74,8 @@ typedef struct {
     int64_t axis_tests;       /* MPC_MODE_COUNT_WORK: full separating-axis evaluations (pairs that passed the cull)*/
     int64_t worklist_overflow;/* 1 if the refinement list had to be grown and the query was re-run                 */
     int64_t box_skipped;      /* MPC_MODE_COUNT_WORK: pairs separated wholesale by a block bounding box            */
+    int64_t done_skipped;     /* MPC_MODE_COUNT_WORK: pairs never looked at because every candidate of their group
+                                 already collided at another time step (the reference's early return)              */
     float tau;                /* float32 uncertainty band used (metres)                                            */
     float ms_device;          /* device time of the kernels of this call (CUDA events on the context's stream)     */
     int32_t ctas;             /* thread blocks of the main kernel                                                  */

@@ -27,7 +27,7 @@ class Stats(C.Structure):
     _fields_ = [("pairs_nominal", C.c_int64), ("refined_fp64", C.c_int64), ("exact_ties", C.c_int64),
                 ("near_tangent", C.c_int64), ("parity_refined", C.c_int64), ("cull_tests", C.c_int64),
                 ("axis_tests", C.c_int64), ("worklist_overflow", C.c_int64), ("box_skipped", C.c_int64),
-                ("tau", C.c_float),
+                ("done_skipped", C.c_int64), ("tau", C.c_float),
                 ("ms_device", C.c_float), ("ctas", C.c_int32), ("kernels", C.c_int32)]
 
     def as_dict(self):

@@ -13,7 +13,7 @@ namespace mpc {
 
 constexpr float BIG = 1e30f;
 constexpr float FAR = 1e18f;
-constexpr int GPC_MAX = 32;       // candidate groups (of 32) per CTA
+constexpr int GPC_MAX = 128;      // candidate groups (of 32) per CTA
 constexpr unsigned FULL = 0xffffffffu;
 
 enum { KIND_OBST = 0, KIND_SEG = 1, KIND_PARITY = 2 };
@@ -29,7 +29,7 @@ struct QDev {
 struct Counters {
     unsigned long long pairs_nominal, refined, exact_ties, near_tangent, parity_refined, cull_tests, axis_tests;
     unsigned wl_count, pad;
-    unsigned long long box_skipped, pad1[7];
+    unsigned long long box_skipped, done_skipped, pad1[6];
 };
 
 struct KParams {
@@ -53,6 +53,7 @@ struct KParams {
     int sg_stride;
     const float *maxabs_scene;
     // queries
+    int cross_exit;              // grid larger than one resident wave: later time slots may use the bits of earlier ones
     const QDev *q;
     const int *cta_off, *cand, *cand_pos, *cand_inv;      // cand_pos: sorted -> caller's position in the set, cand_inv: back
     int B, nwords;
@@ -476,16 +477,20 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    // which (query, slot, chunk) is this CTA
-    // (largest q with cta_off[q] <= blockIdx.x; every warp finds it with warp-wide loads and votes instead of a
-    // chain of dependent loads: a 32-way search per round)
+    // which (slot, query, chunk) is this CTA.  The grid is SLOT-major: all queries' CTAs of time slot 0 come first, then
+    // slot 1, ...  CTAs start in index order, so by the time the later slots of a batch run, the earlier ones have
+    // published their collision bits and whole groups can return early (see `done` below).
+    // (largest q with cta_off[q] <= c; every warp finds it with warp-wide loads and votes instead of a chain of
+    // dependent loads: a 32-way search per round)
+    const int c_total = __ldg(p.cta_off + p.B);                 // CTAs per time slot (sum of the queries' chunks)
+    const int j = (int)blockIdx.x / c_total, cidx = (int)blockIdx.x - j * c_total;
     int q = 0;
     {
         int lo = 0, hi = p.B + 1;                 // answer in [lo, hi)
         while (hi - lo > 1) {
             const int span = hi - lo, stride = (span + 31) >> 5;
             const int idx = lo + lane * stride;
-            const bool le = idx < hi && __ldg(p.cta_off + idx) <= (int)blockIdx.x;
+            const bool le = idx < hi && __ldg(p.cta_off + idx) <= cidx;
             const int k = __popc(__ballot_sync(FULL, le));       // cta_off is sorted: the first k probes are <=
             const int nlo = lo + (k - 1) * stride;
             hi = min(hi, nlo + stride);
@@ -494,9 +499,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
         q = lo;
     }
     const QDev *Q = p.q + q;
-    int local = blockIdx.x - p.cta_off[q];
-    int chunks = Q->chunks;
-    int j = local / chunks, chunk = local - j * chunks;
+    const int chunk = cidx - p.cta_off[q];
     int t = Q->t0 + p.slot_t[j];
     // reference guards: ind + time <= param['steps'] and ind + time < len(space)  (lowLevelPlannerManeuverAutomaton.py:120,122)
     if (t > Q->step_limit || t < 0 || t >= Q->nsteps) return;
@@ -522,10 +525,41 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
     const int nphase = max(1, max(nph_o, nph_s));
     // cull radius shared by the whole CTA: largest library bounding radius + band (conservative for smaller polygons)
     const float rcull = p.lib_rmax + 2.0f * tau;
-    unsigned n_cull = 0, n_axis = 0, n_skip = 0;
+    unsigned n_cull = 0, n_axis = 0, n_skip = 0, n_done = 0;
+    const unsigned *maskp = (Q->pos_base < 0 ? p.mask : p.mask_sorted) + Q->mask_off;
     const int pos_base = Q->pos_base;
     float4 *sA = s_A + warp * FA * 32;
     unsigned *sq = s_q + warp * QCAP;
+
+    // ---- early return of the whole CTA, before any tile is fetched.  In a batch big enough that later time slots start
+    // after earlier ones have finished, the result words already hold the collision bits of those slots: if none of the
+    // CTA's candidates is still undecided there is nothing left to do -- the reference returns at the first violation
+    // too (collision_check :124, collisionChecker.py:22,33).  Only the nominal pair statistic is kept exact.
+    const bool xexit = p.cross_exit && !noexit;
+    unsigned nom = 0;                             // nominal pairs of this warp's groups (one atomic at the end)
+    if (xexit) {
+        bool live = false;
+        for (int g = warp; g < ng; g += NW) {
+            const int ci = (gbeg + g) * 32 + lane;
+            if (ci < cand_cnt && !((__ldcg(maskp + gbeg + g) >> lane) & 1u)) live = true;
+        }
+        if (!__syncthreads_or(live)) {
+            for (int g = warp; g < ng; g += NW) {
+                const int ci = (gbeg + g) * 32 + lane;
+                if (ci < cand_cnt) {
+                    const size_t pj = pos_base >= 0 ? (size_t)j * p.set_total + pos_base + ci
+                                                    : (size_t)__ldg(p.cand + cand_base + ci) * p.J + j;
+                    if (__ldg((pos_base >= 0 ? p.slib_c : p.lib_c) + pj).w > 0.f) nom += (unsigned)(nobst + nseg);
+                }
+            }
+            nom = __reduce_add_sync(FULL, nom);
+            if (lane == 0 && nom) {
+                atomicAdd(&p.cnt->pairs_nominal, (unsigned long long)nom);
+                if (COUNT) atomicAdd(&p.cnt->done_skipped, (unsigned long long)nom);
+            }
+            return;
+        }
+    }
 
     for (int ph = 0; ph < nphase; ph++) {
         const int oc0 = ph * p.cap_o, ocn = max(0, min(nslot - oc0, p.cap_o));       // multiple of 32
@@ -563,6 +597,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
             // ---- lane = one candidate primitive: transform its occupancy polygon, park it in shared memory ----------
             const int ci = (gbeg + g) * 32 + lane;
             bool active = ci < cand_cnt;
+            unsigned done = 0;
             // library record of the lane's candidate: sorted sets have their own copy of the library in set order
             // (consecutive lanes read consecutive 16-byte records); other candidates are gathered through their index
             const bool direct = pos_base >= 0;
@@ -578,6 +613,20 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
             if (active) cc = __ldg((direct ? p.slib_c : p.lib_c) + pj);
             const int nv = (int)cc.w;
             active = active && nv > 0;
+            if (xexit) {
+                // the same test per group: collision bits other time slots have published (L2, not L1).
+                // Every candidate of the group collides at another time step already: the reference returns at the
+                // first violation too (collision_check :124, collisionChecker.py:22,33).
+                done = __ldcg(maskp + gbeg + g);
+                if (__all_sync(FULL, !active || ((done >> lane) & 1u))) {
+                    if (active && ph == 0) {
+                        nom += (unsigned)(nobst + nseg);
+                        if (COUNT) n_done += (unsigned)(nobst + nseg);
+                    }
+                    continue;
+                }
+            }
+            if (active && ph == 0) nom += (unsigned)(nobst + nseg);
             {
                 float ax[VA], ay[VA], ln[((VA * 3 + 3) / 4) * 4];
 #pragma unroll
@@ -610,7 +659,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
             const float acy = active ? fmaf(ls, cc.x, fmaf(lc, cc.y, ly)) : -FAR;
             const float arr = cc.z + 2.0f * tau;
 
-            bool collide = (s_coll[g] >> lane) & 1u;
+            bool collide = ((s_coll[g] | done) >> lane) & 1u;
             bool par = false, punc = false;
             unsigned qn = 0;                        // entries in this warp's queue (warp-uniform)
             // bounding box of the warp's 32 polygon centres: decides which 32-blocks of the spatially sorted obstacle
@@ -621,11 +670,6 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
                 wx0 = warp_min(active ? acx : BIG); wx1 = warp_max(active ? acx : -BIG);
                 wy0 = warp_min(active ? acy : BIG); wy1 = warp_max(active ? acy : -BIG);
                 wr = warp_max(active ? arr : 0.f);
-            }
-
-            if (ph == 0) {   // statistic: nominal pair count of this tile
-                unsigned w = __reduce_add_sync(FULL, active ? (unsigned)(nobst + nseg) : 0u);
-                if (lane == 0 && w) atomicAdd(&p.cnt->pairs_nominal, (unsigned long long)w);
             }
 
             // queue entry = (owner lane << 16) | record index in the tile.  Draining evaluates up to 32 queued pairs at
@@ -886,11 +930,15 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
         }
         if (nphase > 1) __syncthreads();      // everyone is done with the tile before the next bulk copy overwrites it
     }
+    nom = __reduce_add_sync(FULL, nom);
+    if (lane == 0 && nom) atomicAdd(&p.cnt->pairs_nominal, (unsigned long long)nom);
     if (COUNT) {
         n_cull = __reduce_add_sync(FULL, n_cull);
         n_axis = __reduce_add_sync(FULL, n_axis);
         n_skip = __reduce_add_sync(FULL, n_skip);
+        n_done = __reduce_add_sync(FULL, n_done);
         if (lane == 0) {
+            atomicAdd(&p.cnt->done_skipped, (unsigned long long)n_done);
             atomicAdd(&p.cnt->cull_tests, (unsigned long long)n_cull);
             atomicAdd(&p.cnt->axis_tests, (unsigned long long)n_axis);
             atomicAdd(&p.cnt->box_skipped, (unsigned long long)n_skip);

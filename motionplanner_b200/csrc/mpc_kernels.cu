@@ -667,6 +667,8 @@ static KParams make_params(mpc_ctx *ctx) {
     p.sg_stride = ctx->sg_stride;
     p.maxabs_scene = (const float *)ctx->maxabs.p;
     char *qp = (char *)ctx->qpack_d.p;
+    // early return across time slots needs earlier slots to have finished: only grids beyond one resident wave
+    p.cross_exit = ctx->ctas > ctx->prop.multiProcessorCount * K_MIN_CTAS;
     p.q = (const QDev *)qp; p.cta_off = (const int *)(qp + ctx->qpack_cta_off); p.cand = (const int *)ctx->cand_d.p;
     p.cand_pos = (const int *)ctx->sets_pos.p;
     p.cand_inv = p.cand_pos + ctx->set_total;
@@ -757,10 +759,25 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
     const int sms = ctx->prop.multiProcessorCount;
     ctx->threads = K_THREADS;
     const int nwarps = K_THREADS / 32;
-    // groups (of 32 candidates) per CTA: enough CTAs for ~2 waves of 4 CTAs per SM, whole rounds of the CTA's warps
-    int gpc = (int)((total_groups + (long long)sms * 8 - 1) / ((long long)sms * 8));
+    // groups (of 32 candidates) per CTA: enough CTAs for ~2 waves of 4 CTAs per SM (2-4 waves measure the same); big batches get big CTAs (every CTA
+    // pays for its tile: measured 0.78 / 0.49 / 0.40 / 0.33 / 0.30 / 0.29 ms per C4 batch at 4 / 8 / 16 / 32 / 64 / 128
+    // groups).  The count is then evened out over the chunks of the largest query (48 + 48 + 32 is a tail, 43 + 43 + 42
+    // is not).
+    int waves = (mode & MPC_MODE_NO_CULL) ? 6 : 2;      // full evaluation: long uniform CTAs, more of them balance better
+    if (const char *e = getenv("MPC_WAVES")) waves = std::max(1, atoi(e));                       // tuning hook
+    const long long target = (long long)sms * K_MIN_CTAS * waves;
+    int gpc = (int)((total_groups + target - 1) / target);
     gpc = std::max(1, std::min(gpc, GPC_MAX));
-    if (gpc > nwarps / 2) gpc = std::min(GPC_MAX, (gpc + nwarps - 1) / nwarps * nwarps);
+    if (gpc > nwarps / 2 && gpc <= 2 * nwarps) gpc = (gpc + nwarps - 1) / nwarps * nwarps;     // small: whole rounds of the warps
+    {
+        int gmax = 1;
+        for (int q = 0; q < B; q++) gmax = std::max(gmax, (queries[q].cand_cnt + 31) / 32);
+        if (gpc > 2 * nwarps && gpc < gmax) {
+            const int chunks = (gmax + gpc - 1) / gpc;
+            gpc = std::min(GPC_MAX, (gmax + chunks - 1) / chunks);
+        }
+    }
+    if (const char *e = getenv("MPC_GPC")) gpc = std::max(1, std::min(atoi(e), GPC_MAX));      // tuning hook
     ctx->gpc = gpc;
     const int F = ob_fields(ctx->VB), FA = ob_fields(ctx->VA);
     ctx->cap_o = std::max(32, std::min((ctx->max_obst_step + 31) / 32 * 32, ctx->VB == 4 ? 320 : 160));
@@ -800,13 +817,14 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
         o.mask_off = (int)words;
         int groups = (d.cand_cnt + 31) / 32;
         o.chunks = std::max(1, (groups + gpc - 1) / gpc);
-        hcta[q] = (int)ctas;
-        ctas += groups ? (long long)o.chunks * ctx->J : 0;
+        hcta[q] = (int)ctas;                      // per time slot: the grid is slot-major, ctas * J blocks in all
+        ctas += groups ? (long long)o.chunks : 0;
         words += groups;
         maxq = std::max(maxq, std::max(std::fabs(d.x - ox), std::fabs(d.y - oy)) + ctx->lib_radius);
         if (!(std::fabs(d.c) <= 1.0000001 && std::fabs(d.s) <= 1.0000001)) return fail(ctx, MPC_E_ARG, "query %d: (c, s) is not a rotation", q);
     }
     hcta[B] = (int)ctas;
+    ctas *= ctx->J;
     if (ctas > 0x7fffffffLL || words > 0x7fffffffLL) return fail(ctx, MPC_E_LIMIT, "batch too large");
     if (ncand) memcpy(hidx, cand_idx, bytes_i);
     ctx->maxabs_query = std::nextafter((float)maxq, INFINITY);
@@ -858,6 +876,7 @@ static void fill_stats(mpc_ctx *ctx, mpc_stats *st, float ms, int kernels, int o
     st->cull_tests = (int64_t)c.cull_tests;
     st->axis_tests = (int64_t)c.axis_tests;
     st->box_skipped = (int64_t)c.box_skipped;
+    st->done_skipped = (int64_t)c.done_skipped;
     st->worklist_overflow = overflow;
     st->ms_device = ms;
     st->ctas = ctx->ctas;
