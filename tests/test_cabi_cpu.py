@@ -31,7 +31,7 @@ def test_struct_layouts_match_header():
     assert _cabi.QUERY_DTYPE.itemsize == 64
     assert [_cabi.QUERY_DTYPE.fields[k][1] for k in ("x", "y", "c", "s", "scene", "t0", "step_limit", "cand_set",
                                                       "cand_off", "cand_cnt")] == [0, 8, 16, 24, 32, 36, 40, 44, 48, 52]
-    assert C.sizeof(_cabi.Stats) == 9 * 8 + 4 * 4
+    assert C.sizeof(_cabi.Stats) == 10 * 8 + 4 * 4
     assert C.sizeof(_cabi.DevInfo) == 64 + 4 * 4 + 8 + 4 + 4
 
 
