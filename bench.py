@@ -310,7 +310,9 @@ def main():
             "config": {"workload": WORKLOAD, "queries_per_step": nq,
                        "queries_what": "one step = one batch of ego poses (seed 2 jitter) against one staged scene",
                        "checks_per_step": checks_step, "seeds": [0, 1, 2], "l2": "flushed before every timed step "
-                       "(256 MiB fill)", "early_exit": "warp-wide per tile", "parallelism": "replicated library, "
+                       "(256 MiB fill)", "early_exit": "reference semantics (return at the first violation): warp-wide per tile, and whole "
+                       "groups / CTAs whose candidates already collide at another time step skip their tile; the "
+                       "no-exit, no-cull rate is roofline.full_evaluation", "parallelism": "replicated library, "
                        "queries sharded per GPU, no collective on the hot path"},
             "e2e": {"value": world * args.steps * checks_step / e2e_s, "unit": "checks/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -335,7 +337,11 @@ def main():
                                "figure)",
                 "kernel_ms": main_ms,
                 "executed": {"cull_axis_tests": st_cnt["cull_tests"], "full_sat_tests": st_cnt["axis_tests"],
-                             "pairs_separated_by_block_box": st_cnt["box_skipped"], "flop": exec_flop},
+                             "pairs_separated_by_block_box": st_cnt["box_skipped"],
+                             "pairs_skipped_after_collision_at_another_step": st_cnt["done_skipped"],
+                             "pairs_nominal": st_cnt["pairs_nominal"], "flop": exec_flop,
+                             "note": "instrumented launch of the same batch; which tiles are skipped depends on "
+                                     "scheduling, the decisions do not"},
                 "algorithmic_survey": {"flop_per_check": FLOP_PER_CHECK, "achieved": algo_tflops,
                                        "frac": algo_tflops / FP32_PEAK_TFLOPS,
                                        "note": "SURVEY.md 8(d) definition: 304 flop x checks / time. Above 1 by "

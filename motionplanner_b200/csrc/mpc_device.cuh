@@ -14,6 +14,7 @@ namespace mpc {
 constexpr float BIG = 1e30f;
 constexpr float FAR = 1e18f;
 constexpr int GPC_MAX = 128;      // candidate groups (of 32) per CTA
+static_assert(GPC_MAX <= 128, "the compaction scan gives every lane of one warp four words");
 constexpr unsigned FULL = 0xffffffffu;
 
 enum { KIND_OBST = 0, KIND_SEG = 1, KIND_PARITY = 2 };
@@ -53,6 +54,7 @@ struct KParams {
     int sg_stride;
     const float *maxabs_scene;
     // queries
+    int compact;                 // renumber the undecided candidates densely (needs: every library slot occupied, big CTAs)
     int cross_exit;              // grid larger than one resident wave: later time slots may use the bits of earlier ones
     const QDev *q;
     const int *cta_off, *cand, *cand_pos, *cand_inv;      // cand_pos: sorted -> caller's position in the set, cand_inv: back
@@ -537,7 +539,50 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
     // too (collision_check :124, collisionChecker.py:22,33).  Only the nominal pair statistic is kept exact.
     const bool xexit = p.cross_exit && !noexit;
     unsigned nom = 0;                             // nominal pairs of this warp's groups (one atomic at the end)
-    if (xexit) {
+    // Compaction: when every library slot is occupied (so "candidate" = "occupancy present") and the step fits one tile,
+    // the undecided candidates of the CTA are renumbered densely -- groups are formed from the live ones only, instead
+    // of running every group that still has one straggler.  s_par / s_punc (multi-phase state, unused here) hold the
+    // live words and their running counts.
+    const bool cmode = xexit && p.compact && nphase == 1;
+    unsigned *s_live = s_par, *s_pref = s_punc;
+    int total_live = 0;
+    if (cmode) {
+        if (warp == 0) {
+            unsigned cnt[4], run = 0;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {          // lane owns words 4*lane .. 4*lane+3 (GPC_MAX = 128)
+                const int i = 4 * lane + r;
+                unsigned live = 0;
+                if (i < ng) {
+                    const int nvalid = min(32, cand_cnt - (gbeg + i) * 32);
+                    const unsigned valid = nvalid >= 32 ? FULL : ((1u << nvalid) - 1u);
+                    live = valid & ~__ldcg(maskp + gbeg + i);
+                    s_live[i] = live;
+                }
+                cnt[r] = run;
+                run += __popc(live);
+            }
+            unsigned incl = run;                    // inclusive scan of the lanes' sums
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const unsigned excl = incl - run;
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                if (4 * lane + r < ng) s_pref[4 * lane + r] = excl + cnt[r];
+            if (lane == 31) s_coll[0] = incl;
+        }
+        __syncthreads();
+        total_live = (int)s_coll[0];
+        if (tid == 0) {                              // the statistic needs no library access here
+            const unsigned long long w = (unsigned long long)min(ng * 32, cand_cnt - gbeg * 32) * (unsigned)(nobst + nseg);
+            atomicAdd(&p.cnt->pairs_nominal, w);
+            if (COUNT) atomicAdd(&p.cnt->done_skipped, (unsigned long long)(min(ng * 32, cand_cnt - gbeg * 32) - total_live) * (unsigned)(nobst + nseg));
+        }
+        if (total_live == 0) return;                 // nothing undecided: the reference has returned already
+    } else if (xexit) {
         bool live = false;
         for (int g = warp; g < ng; g += NW) {
             const int ci = (gbeg + g) * 32 + lane;
@@ -560,6 +605,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
             return;
         }
     }
+    const int ngl = cmode ? (total_live + 31) / 32 : ng;      // groups this CTA runs
 
     for (int ph = 0; ph < nphase; ph++) {
         const int oc0 = ph * p.cap_o, ocn = max(0, min(nslot - oc0, p.cap_o));       // multiple of 32
@@ -591,12 +637,23 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
         int nxt_prim = 0;
         {
             const int ci0 = (gbeg + warp) * 32 + lane;
-            if (pos_base < 0 && warp < ng && ci0 < cand_cnt) nxt_prim = __ldg(p.cand + cand_base + ci0);
+            if (!cmode && pos_base < 0 && warp < ng && ci0 < cand_cnt) nxt_prim = __ldg(p.cand + cand_base + ci0);
         }
-        for (int g = warp; g < ng; g += NW) {
+        for (int g = warp; g < ngl; g += NW) {
             // ---- lane = one candidate primitive: transform its occupancy polygon, park it in shared memory ----------
-            const int ci = (gbeg + g) * 32 + lane;
+            int ci = (gbeg + g) * 32 + lane;
             bool active = ci < cand_cnt;
+            if (cmode) {
+                // the lane's rank among the CTA's undecided candidates -> word (bisection on the running counts) -> bit
+                const int rk = g * 32 + lane;
+                active = rk < total_live;
+                int lo = 0, hi = ng;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if ((int)s_pref[mid] <= rk) lo = mid; else hi = mid;
+                }
+                ci = active ? (gbeg + lo) * 32 + (int)__fns(s_live[lo], 0, rk - (int)s_pref[lo] + 1) : 0;
+            }
             unsigned done = 0;
             // library record of the lane's candidate: sorted sets have their own copy of the library in set order
             // (consecutive lanes read consecutive 16-byte records); other candidates are gathered through their index
@@ -604,8 +661,9 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
             const float4 *Lv = direct ? p.slib_v : p.lib_v, *Ln = direct ? p.slib_n : p.lib_n;
             const size_t fstride = direct ? (size_t)p.J * p.set_total : (size_t)p.PJ;
             size_t pj = 0;
+            if (cmode && !direct && active) nxt_prim = __ldg(p.cand + cand_base + ci);
             if (active) pj = direct ? (size_t)j * p.set_total + pos_base + ci : (size_t)nxt_prim * p.J + j;
-            if (!direct) {
+            if (!direct && !cmode) {
                 const int cin = ci + NW * 32;
                 if (g + NW < ng && cin < cand_cnt) nxt_prim = __ldg(p.cand + cand_base + cin);
             }
@@ -613,7 +671,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
             if (active) cc = __ldg((direct ? p.slib_c : p.lib_c) + pj);
             const int nv = (int)cc.w;
             active = active && nv > 0;
-            if (xexit) {
+            if (xexit && !cmode) {
                 // the same test per group: collision bits other time slots have published (L2, not L1).
                 // Every candidate of the group collides at another time step already: the reference returns at the
                 // first violation too (collision_check :124, collisionChecker.py:22,33).
@@ -626,7 +684,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
                     continue;
                 }
             }
-            if (active && ph == 0) nom += (unsigned)(nobst + nseg);
+            if (!cmode && active && ph == 0) nom += (unsigned)(nobst + nseg);
             {
                 float ax[VA], ay[VA], ln[((VA * 3 + 3) / 4) * 4];
 #pragma unroll
@@ -659,7 +717,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
             const float acy = active ? fmaf(ls, cc.x, fmaf(lc, cc.y, ly)) : -FAR;
             const float arr = cc.z + 2.0f * tau;
 
-            bool collide = ((s_coll[g] | done) >> lane) & 1u;
+            bool collide = cmode ? false : (((s_coll[g] | done) >> lane) & 1u);
             bool par = false, punc = false;
             unsigned qn = 0;                        // entries in this warp's queue (warp-uniform)
             // bounding box of the warp's 32 polygon centres: decides which 32-blocks of the spatially sorted obstacle
@@ -715,7 +773,8 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
                     if (COUNT) n_axis++;
                 }
                 const bool hit = have && sep < -tau;
-                if (have && !hit && !(sep > tau)) push_work(p, q, (gbeg + g) * 32 + src, j, KIND_OBST, o0 + oc0 + slot);
+                const int ci_src = __shfl_sync(FULL, ci, src);
+                if (have && !hit && !(sep > tau)) push_work(p, q, ci_src, j, KIND_OBST, o0 + oc0 + slot);
                 const unsigned m = __reduce_or_sync(FULL, hit ? (1u << src) : 0u);
                 collide |= (m >> lane) & 1u;
             };
@@ -731,7 +790,8 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
                     if (COUNT) n_axis++;
                 }
                 const bool hit = have && sep < -tau;
-                if (have && !hit && !(sep > tau)) push_work(p, q, (gbeg + g) * 32 + src, j, KIND_SEG, g0 + sc0 + k);
+                const int ci_src = __shfl_sync(FULL, ci, src);
+                if (have && !hit && !(sep > tau)) push_work(p, q, ci_src, j, KIND_SEG, g0 + sc0 + k);
                 const unsigned m = __reduce_or_sync(FULL, hit ? (1u << src) : 0u);
                 collide |= (m >> lane) & 1u;
             };
@@ -919,12 +979,13 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
                     if ((bu >> lane) & 1u) push_work(p, q, ci, j, KIND_PARITY, 0);
                     else if (!((bp >> lane) & 1u)) coll = true;        // centre outside the region
                 }
-                if (pos_base < 0) {
+                // spatially sorted candidate sets: bits in sorted order, k_refine moves them home
+                unsigned *out = (pos_base < 0 ? p.mask : p.mask_sorted) + Q->mask_off;
+                if (cmode) {    // compacted group: every lane has its own word
+                    if (coll && active) atomicOr(out + (ci >> 5), 1u << (ci & 31));
+                } else {
                     unsigned word = __ballot_sync(FULL, coll && active);
-                    if (lane == 0 && word) atomicOr(p.mask + Q->mask_off + gbeg + g, word);
-                } else {        // spatially sorted candidate set: bits in sorted order, k_refine moves them home
-                    unsigned word = __ballot_sync(FULL, coll && active);
-                    if (lane == 0 && word) atomicOr(p.mask_sorted + Q->mask_off + gbeg + g, word);
+                    if (lane == 0 && word) atomicOr(out + gbeg + g, word);
                 }
             }
         }
