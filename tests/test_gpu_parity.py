@@ -383,3 +383,52 @@ def test_adversarial_with_sorted_sets_and_block_culling(eng, mode):
     stage(eng, lib, sc, org)
     g2, st2 = eng.query(q, None, mode | MODE_COUNT_WORK | MODE_NO_EARLY_EXIT)
     assert st2["box_skipped"] > 0 and st2["cull_tests"] + st2["box_skipped"] + 0 >= 0
+
+
+def test_early_return_across_time_slots_and_compaction(eng):
+    """big batches run slot-major and skip tiles whose candidates already collide at another time step (the reference's
+    early return); with a fully occupied library the undecided candidates are renumbered densely.  Every regime must
+    give the oracle's bits and the exact nominal pair count: whole sorted sets (compaction), partial ranges and explicit
+    lists (group-level skip), a library with empty slots (no compaction), validator mode, and no-exit mode."""
+    lib, sc, org, q = W.c4_problem(nqueries=12)
+    P = lib["verts"].shape[0]
+    pb = orc.Problem(lib, sc)
+    stage(eng, lib, sc, org)
+    # (a) whole sets: 12 x 128 groups x 50 slots -> 128 groups per CTA, compaction on
+    for mode, omode in ((MODE_PLANNER, 0), (MODE_VALIDATOR, orc.MODE_STRICT)):
+        got, st = eng.query(q, None, mode)
+        want, ost = pb.check(q, None, omode, inner_parallel=True)
+        assert np.array_equal(got, want)
+        assert st["pairs_nominal"] == ost["pairs_nominal"] == 12 * P * 50 * (256 + 4)
+    base = got
+    noexit, st_ne = eng.query(q, None, MODE_VALIDATOR | MODE_NO_EARLY_EXIT)
+    assert np.array_equal(noexit, base)
+    cnt, st_c = eng.query(q, None, MODE_VALIDATOR | MODE_COUNT_WORK)
+    assert np.array_equal(cnt, base)
+    assert st_c["done_skipped"] > 0.3 * st_c["pairs_nominal"]                 # most of the work is never looked at
+    assert st_c["done_skipped"] + st_c["box_skipped"] + st_c["cull_tests"] <= st_c["pairs_nominal"]
+    # (b) ragged: partial ranges of the set, explicit lists, empty queries -- the group-level skip without compaction
+    rng = np.random.default_rng(4)
+    cand = rng.permutation(P).astype(np.int32)
+    q2 = np.concatenate([q, q, q[:6]])
+    for k in range(len(q2)):
+        if k % 3 == 0:
+            q2[k]["cand_off"], q2[k]["cand_cnt"] = 100 + k, P - 300 - 7 * k              # range inside the staged set
+        elif k % 3 == 1:
+            q2[k]["cand_set"], q2[k]["cand_off"], q2[k]["cand_cnt"] = -1, 5 * k, P - 5 * k   # explicit list
+        if k == 7:
+            q2[k]["cand_cnt"] = 0
+    got, st = eng.query(q2, cand, MODE_PLANNER)
+    want, ost = pb.check(q2, cand, 0, inner_parallel=True)
+    assert np.array_equal(got, want) and st["pairs_nominal"] == ost["pairs_nominal"]
+    # (c) a library with holes: every 5th occupancy of every 3rd primitive is missing -> statistic needs the library
+    lib2 = dict(lib, nv=lib["nv"].copy())
+    lib2["nv"][::3, ::5] = 0
+    stage(eng, lib2, sc, org)
+    got, st = eng.query(q, None, MODE_PLANNER)
+    want, ost = orc.Problem(lib2, sc).check(q, None, 0, inner_parallel=True)
+    assert np.array_equal(got, want) and st["pairs_nominal"] == ost["pairs_nominal"]
+    # repeatability: which tiles are skipped depends on scheduling, the bits must not
+    for _ in range(5):
+        again, _ = eng.query(q, None, MODE_PLANNER)
+        assert np.array_equal(again, got)
