@@ -140,6 +140,17 @@ __device__ __forceinline__ void atomic_max_pos_float(float *addr, float v) {
     atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
 }
 
+// position of the n-th (0-based) set bit of x; x must have more than n bits set
+__device__ __forceinline__ int nth_set_bit(unsigned x, unsigned n) {
+    int pos = 0;
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const unsigned c = __popc(x & ((1u << w) - 1u));
+        if (n >= c) { n -= c; x >>= w; pos += w; }
+    }
+    return pos;
+}
+
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));
@@ -544,7 +555,8 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
     // of running every group that still has one straggler.  s_par / s_punc (multi-phase state, unused here) hold the
     // live words and their running counts.
     const bool cmode = xexit && p.compact && nphase == 1;
-    unsigned *s_live = s_par, *s_pref = s_punc;
+    unsigned *s_live = s_par, *s_pref = s_punc, *s_gstart = s_coll;       // s_gstart[g]: word holding rank 32 g
+    unsigned *s_tot = reinterpret_cast<unsigned *>(smem_raw + 8);          // (the mbarrier uses bytes 0..7)
     int total_live = 0;
     if (cmode) {
         if (warp == 0) {
@@ -570,12 +582,20 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
             }
             const unsigned excl = incl - run;
 #pragma unroll
-            for (int r = 0; r < 4; r++)
-                if (4 * lane + r < ng) s_pref[4 * lane + r] = excl + cnt[r];
-            if (lane == 31) s_coll[0] = incl;
+            for (int r = 0; r < 4; r++) {
+                const int i = 4 * lane + r;
+                if (i < ng) {
+                    const unsigned a = excl + cnt[r], n = (r < 3 ? excl + cnt[r + 1] : incl) - a;     // ranks [a, a + n)
+                    s_pref[i] = a;
+                    // at most one multiple of 32 falls into a word's rank range: the word where that group starts
+                    const unsigned gfirst = (a + 31u) >> 5;
+                    if (gfirst * 32u < a + n) s_gstart[gfirst] = (unsigned)i;
+                }
+            }
+            if (lane == 31) *s_tot = incl;
         }
         __syncthreads();
-        total_live = (int)s_coll[0];
+        total_live = (int)*s_tot;
         if (tid == 0) {                              // the statistic needs no library access here
             const unsigned long long w = (unsigned long long)min(ng * 32, cand_cnt - gbeg * 32) * (unsigned)(nobst + nseg);
             atomicAdd(&p.cnt->pairs_nominal, w);
@@ -647,12 +667,12 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
                 // the lane's rank among the CTA's undecided candidates -> word (bisection on the running counts) -> bit
                 const int rk = g * 32 + lane;
                 active = rk < total_live;
-                int lo = 0, hi = ng;
+                int lo = (int)s_gstart[g], hi = (g + 1 < ngl) ? (int)s_gstart[g + 1] + 1 : ng;    // usually 1-2 words
                 while (hi - lo > 1) {
                     const int mid = (lo + hi) >> 1;
                     if ((int)s_pref[mid] <= rk) lo = mid; else hi = mid;
                 }
-                ci = active ? (gbeg + lo) * 32 + (int)__fns(s_live[lo], 0, rk - (int)s_pref[lo] + 1) : 0;
+                ci = active ? (gbeg + lo) * 32 + nth_set_bit(s_live[lo], (unsigned)(rk - (int)s_pref[lo])) : 0;
             }
             unsigned done = 0;
             // library record of the lane's candidate: sorted sets have their own copy of the library in set order
