@@ -54,6 +54,7 @@ struct KParams {
     int sg_stride;
     const float *maxabs_scene;
     // queries
+    int c_total;                 // CTAs per time slot: the grid is c_total * J blocks, slot-major
     int compact;                 // renumber the undecided candidates densely (needs: every library slot occupied, big CTAs)
     int cross_exit;              // grid larger than one resident wave: later time slots may use the bits of earlier ones
     const QDev *q;
@@ -495,7 +496,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
     // published their collision bits and whole groups can return early (see `done` below).
     // (largest q with cta_off[q] <= c; every warp finds it with warp-wide loads and votes instead of a chain of
     // dependent loads: a 32-way search per round)
-    const int c_total = __ldg(p.cta_off + p.B);                 // CTAs per time slot (sum of the queries' chunks)
+    const int c_total = p.c_total;                              // CTAs per time slot (sum of the queries' chunks)
     const int j = (int)blockIdx.x / c_total, cidx = (int)blockIdx.x - j * c_total;
     int q = 0;
     {
@@ -554,7 +555,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
     // the undecided candidates of the CTA are renumbered densely -- groups are formed from the live ones only, instead
     // of running every group that still has one straggler.  s_par / s_punc (multi-phase state, unused here) hold the
     // live words and their running counts.
-    const bool cmode = xexit && p.compact && nphase == 1;
+    const bool cmode = xexit && p.compact && nphase == 1 && ng >= 32;      // the pre-pass pays from ~32 groups on
     unsigned *s_live = s_par, *s_pref = s_punc, *s_gstart = s_coll;       // s_gstart[g]: word holding rank 32 g
     unsigned *s_tot = reinterpret_cast<unsigned *>(smem_raw + 8);          // (the mbarrier uses bytes 0..7)
     int total_live = 0;

@@ -673,6 +673,7 @@ static KParams make_params(mpc_ctx *ctx) {
     // (C4, ms per batch of 4 / 8 / 16 / 64 queries: 0.073 / 0.085 / 0.111 / 0.219 with, 0.066 / 0.088 / 0.123 / 0.307 without)
     p.compact = (ctx->lib_full && ctx->gpc >= 32) ? 1 : 0;
     if (getenv("MPC_NO_COMPACT")) p.compact = 0;                                                // tuning hook
+    p.c_total = ctx->J > 0 ? ctx->ctas / ctx->J : 0;
     p.cross_exit = ctx->ctas > ctx->prop.multiProcessorCount * K_MIN_CTAS;
     p.q = (const QDev *)qp; p.cta_off = (const int *)(qp + ctx->qpack_cta_off); p.cand = (const int *)ctx->cand_d.p;
     p.cand_pos = (const int *)ctx->sets_pos.p;
