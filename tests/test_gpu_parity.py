@@ -432,3 +432,20 @@ def test_early_return_across_time_slots_and_compaction(eng):
     for _ in range(5):
         again, _ = eng.query(q, None, MODE_PLANNER)
         assert np.array_equal(again, got)
+
+
+def test_early_return_with_multi_phase_tiles(eng):
+    """768 obstacles per step do not fit one tile (cap 320): the step is processed in phases, and in a batch of more
+    than one resident wave the group-level early return acts between them"""
+    lib, sc, org, q = W.c4_problem(P=1024, O_lanes=8, slots=96, T=10, nqueries=24)
+    stage(eng, lib, sc, org)
+    pb = orc.Problem(lib, sc)
+    for mode, omode in ((MODE_PLANNER, 0), (MODE_VALIDATOR, orc.MODE_STRICT)):
+        got, st = eng.query(q, None, mode)
+        want, ost = pb.check(q, None, omode, inner_parallel=True)
+        assert np.array_equal(got, want)
+        assert st["pairs_nominal"] == ost["pairs_nominal"] == 24 * 1024 * 10 * (768 + 4)
+    assert st["ctas"] > 148 * 4
+    noexit, _ = eng.query(q, None, MODE_VALIDATOR | MODE_NO_EARLY_EXIT)
+    assert np.array_equal(noexit, got)
+    assert 0.02 < got.mean() < 0.999
