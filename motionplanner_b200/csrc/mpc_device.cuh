@@ -334,6 +334,76 @@ __global__ void k_stage_obst(int nslots, const double *__restrict__ src64, const
                                         __fadd_ru(x1, 1e-6f * fabsf(x1)), __fadd_ru(y1, 1e-6f * fabsf(y1)));
 }
 
+// Large scene sets: one CTA per distinct segment range sorts it along a Morton curve of the segment midpoints (the same
+// order the host computes for small sets, mpc_set_scenes pass 2) and writes the 32-aligned, padded slot range: float64
+// segments for the tie-break pass and the owning scene per slot.  Ranges longer than SEG_SORT_MAX stay on the host.
+constexpr int SEG_SORT_MAX = 4096;
+__global__ void __launch_bounds__(256) k_order_segs(const int4 *__restrict__ jobs, const double *__restrict__ raw,
+                                                    double *__restrict__ sg64, int *__restrict__ seg_scene) {
+    __shared__ unsigned s_key[SEG_SORT_MAX];
+    __shared__ unsigned short s_idx[SEG_SORT_MAX];
+    __shared__ double s_red[4][8];
+    const int4 J = jobs[blockIdx.x];                       // (begin, end, scene, first slot)
+    const int n = J.y - J.x, padded = (n + 31) / 32 * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double *g = raw + 4 * (size_t)(J.x + i);
+        const double mx = 0.5 * (g[0] + g[2]), my = 0.5 * (g[1] + g[3]);
+        x0 = fmin(x0, mx); x1 = fmax(x1, mx); y0 = fmin(y0, my); y1 = fmax(y1, my);
+    }
+    for (int o = 16; o; o >>= 1) {
+        x0 = fmin(x0, __shfl_xor_sync(FULL, x0, o)); x1 = fmax(x1, __shfl_xor_sync(FULL, x1, o));
+        y0 = fmin(y0, __shfl_xor_sync(FULL, y0, o)); y1 = fmax(y1, __shfl_xor_sync(FULL, y1, o));
+    }
+    if (lane == 0) { s_red[0][warp] = x0; s_red[1][warp] = x1; s_red[2][warp] = y0; s_red[3][warp] = y1; }
+    __syncthreads();
+    for (int w = 0; w < 8; w++) {
+        x0 = fmin(x0, s_red[0][w]); x1 = fmax(x1, s_red[1][w]); y0 = fmin(y0, s_red[2][w]); y1 = fmax(y1, s_red[3][w]);
+    }
+    const double sx = (x1 > x0) ? 65535.0 / (x1 - x0) : 0.0, sy = (y1 > y0) ? 65535.0 / (y1 - y0) : 0.0;
+    int n2 = 32;
+    while (n2 < n) n2 <<= 1;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        unsigned key = 0xffffffffu;
+        if (i < n) {
+            const double *g = raw + 4 * (size_t)(J.x + i);
+            const double mx = 0.5 * (g[0] + g[2]), my = 0.5 * (g[1] + g[3]);
+            key = morton16_dev((unsigned)((mx - x0) * sx), (unsigned)((my - y0) * sy));
+        }
+        s_key[i] = key;
+        s_idx[i] = (unsigned short)i;
+    }
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                const int l = i ^ jj;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const unsigned a = s_key[i], b = s_key[l];
+                    const bool gt = a > b || (a == b && s_idx[i] > s_idx[l]);      // ties by source index: deterministic
+                    if (gt == up) {
+                        s_key[i] = b; s_key[l] = a;
+                        const unsigned short t = s_idx[i]; s_idx[i] = s_idx[l]; s_idx[l] = t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < padded; i += blockDim.x) {
+        double *dst = sg64 + 4 * (size_t)(J.w + i);
+        if (i < n) {
+            const double *g = raw + 4 * (size_t)(J.x + s_idx[i]);
+            dst[0] = g[0]; dst[1] = g[1]; dst[2] = g[2]; dst[3] = g[3];
+            seg_scene[J.w + i] = J.z;
+        } else {
+            dst[0] = dst[1] = dst[2] = dst[3] = 0.0;
+            seg_scene[J.w + i] = -1;
+        }
+    }
+}
+
 // one thread per segment slot (slots are laid out in 32-aligned, spatially sorted ranges by the host); a warp = one
 // block of 32 slots and also reduces the block's bounding box (of the float32 data the main kernel will see)
 __global__ void k_stage_segs(int nslots, const double *__restrict__ sg64, const int *__restrict__ seg_scene,
