@@ -11,6 +11,7 @@ from helpers import OracleBackend, load_golden, random_walk, scenario_scene
 from motionplanner_b200.checker import PrimitiveChecker, SceneSet, car_library, validate_trajectory
 from motionplanner_b200.engine import MODE_PLANNER, MODE_VALIDATOR, CollisionEngine, make_queries
 from motionplanner_b200.maneuverAutomaton.createManeuverAutomaton import load_maneuver_automaton
+from oracle import oracle as orc
 
 
 @pytest.fixture(scope="module")
@@ -96,4 +97,54 @@ def test_validator_on_scenarios(MA, golden):
         steps += len(res[0])
         flagged += int(res[1].sum())
     assert steps > 500 and 0 < flagged < steps
+    eng.close()
+
+
+def test_batch_of_scenes_with_device_side_segment_sort(MA, golden):
+    """300 scenario-shaped queries against 300 scenes staged in ONE mpc_set_scenes call (the C5 shape): more than 8192
+    boundary segments in all, so the ranges are Morton-sorted by k_order_segs on the device instead of on the host"""
+    from motionplanner_b200.engine import CollisionEngine, make_queries
+    rng = np.random.default_rng(3)
+    names = sorted(golden)
+    lay = MA.device_layout(0.1)
+    scenes = SceneSet()
+    q = make_queries(300)
+    draw = rng.integers(0, len(names), 300)
+    for k, gi in enumerate(draw):
+        g = golden[names[gi]]
+        n = min(g['nsteps'], 31)
+        off = g['step_obst_off'][:n + 1]
+        segs = g['road_safe'] if len(g['road_safe']) else g['road']
+        scenes.add_scene_explicit(n, off, g['obst'][:off[-1]], g['obst_nv'][:off[-1]], segs, origin=g['x0'][0:2])
+        x0 = g['x0']
+        bucket = int(MA._bucket(x0[2]))
+        q[k] = (x0[0] - np.cos(x0[3]) * 1.15, x0[1] - np.sin(x0[3]) * 1.15, np.cos(x0[3]), np.sin(x0[3]), k, 0,
+                g['t_end'], bucket, 0, len(MA.vel_dic[bucket]), 0, 0)
+    arrays = scenes.arrays()
+    assert len(arrays['segs']) >= 8192 and max(arrays['step_seg_end'] - arrays['step_seg_begin']) <= 4096
+    eng = CollisionEngine(0)
+    eng.upload_library(lay['verts'], lay['nv'], lay['tidx'], lay['set_off'], lay['set_idx'])
+    eng.set_scenes(arrays['scene_step_off'], arrays['origins'], arrays['step_obst_off'], arrays['obst'],
+                   arrays['obst_nv'], arrays['step_seg_begin'], arrays['step_seg_end'], arrays['segs'])
+    got, st = eng.query(q)
+    lib = dict(verts=lay['verts'], nv=lay['nv'], tidx=lay['tidx'], set_off=lay['set_off'], set_idx=lay['set_idx'])
+    want, ost = orc.Problem(lib, arrays).check(q, None, orc.MODE_NO_EARLY_EXIT)
+    assert np.array_equal(got, want) and st['pairs_nominal'] == ost['pairs_nominal']
+    assert 0.2 < got.mean() < 0.95
+    # the same scenes staged one at a time go through the host-side sort: same bits
+    for k in (0, 17, 123, 299):
+        one = SceneSet()
+        g = golden[names[draw[k]]]
+        n = min(g['nsteps'], 31)
+        off = g['step_obst_off'][:n + 1]
+        segs = g['road_safe'] if len(g['road_safe']) else g['road']
+        one.add_scene_explicit(n, off, g['obst'][:off[-1]], g['obst_nv'][:off[-1]], segs, origin=g['x0'][0:2])
+        a1 = one.arrays()
+        eng.set_scenes(a1['scene_step_off'], a1['origins'], a1['step_obst_off'], a1['obst'], a1['obst_nv'],
+                       a1['step_seg_begin'], a1['step_seg_end'], a1['segs'])
+        qk = q[k:k + 1].copy()
+        qk['scene'] = 0
+        bits, _ = eng.query(qk)
+        lo = int(q['cand_cnt'][:k].sum())
+        assert np.array_equal(bits, got[lo:lo + int(q['cand_cnt'][k])])
     eng.close()
