@@ -16,7 +16,6 @@ child then only applies the time guard of the reference (:99-109) and reads the 
 import operator
 
 import numpy as np
-import scipy.linalg
 
 from ..checker import PrimitiveChecker, SceneSet
 from ..geometry import Point
@@ -57,7 +56,10 @@ class Node:
 
 
 def _rotation(phi):
-    return scipy.linalg.block_diag(np.array([[np.cos(phi), -np.sin(phi)], [np.sin(phi), np.cos(phi)]]), np.eye(2))
+    """block_diag([[cos, -sin], [sin, cos]], eye(2)) of the reference (:44, :75), built directly (the scipy call costs
+    100 us per expansion)"""
+    c, s = np.cos(phi), np.sin(phi)
+    return np.array([[c, -s, 0.0, 0.0], [s, c, 0.0, 0.0], [0.0, 0.0, 1.0, 0.0], [0.0, 0.0, 0.0, 1.0]])
 
 
 def expand_node(node, primitive, ind, ref_traj, fixed, T, collides=None):
