@@ -449,3 +449,35 @@ def test_early_return_with_multi_phase_tiles(eng):
     noexit, _ = eng.query(q, None, MODE_VALIDATOR | MODE_NO_EARLY_EXIT)
     assert np.array_equal(noexit, got)
     assert 0.02 < got.mean() < 0.999
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_randomised_batch_shapes_against_oracle(eng, seed):
+    """random batch shapes around the regime switches of the launch heuristics (groups per CTA, chunks per query, slot-
+    major grid, early return with and without compaction, tiles in one or several phases): library size, horizon,
+    obstacles per step, batch size, ragged candidate ranges, start indices and step limits are all drawn at random;
+    bits and the nominal pair count must equal the oracle's in planner and validator mode"""
+    rng = np.random.default_rng(1000 + seed)
+    P = int(rng.choice([160, 500, 1024, 2080, 3000]))
+    T = int(rng.integers(3, 14))
+    slots = int(rng.choice([4, 12, 32, 45]))
+    B = int(rng.choice([1, 3, 9, 20, 40]))
+    lib, sc, org, q = W.c4_problem(P=P, O_lanes=8, slots=slots, T=T, nqueries=B)
+    for k in range(B):
+        r = rng.random()
+        if r < 0.3:                                   # a range inside the (single) staged set
+            lo = int(rng.integers(0, P // 2))
+            q[k]["cand_off"], q[k]["cand_cnt"] = lo, int(rng.integers(0, P - lo + 1))
+        elif r < 0.5:                                 # explicit list
+            lo = int(rng.integers(0, P // 2))
+            q[k]["cand_set"], q[k]["cand_off"], q[k]["cand_cnt"] = -1, lo, int(rng.integers(1, P - lo + 1))
+        q[k]["t0"] = int(rng.integers(0, 3))
+        q[k]["step_limit"] = int(rng.choice([T + 5, T - 2, 1]))
+    cand = rng.permutation(P).astype(np.int32)
+    stage(eng, lib, sc, org)
+    pb = orc.Problem(lib, sc)
+    for mode, omode in ((MODE_PLANNER, 0), (MODE_VALIDATOR, orc.MODE_STRICT)):
+        got, st = eng.query(q, cand, mode)
+        want, ost = pb.check(q, cand, omode | orc.MODE_NO_EARLY_EXIT)
+        assert np.array_equal(got, want), (P, T, slots, B, mode)
+        assert st["pairs_nominal"] == ost["pairs_nominal"], (P, T, slots, B, mode)
