@@ -90,7 +90,6 @@ struct mpc_ctx {
     std::map<std::vector<long long>, cudaGraphExec_t> graphs;
     void *h_res = nullptr;
     size_t h_res_cap = 0;
-    std::map<int, size_t> smem_attr;
     int wl_cap = 0;
     void *h_pin = nullptr;
     size_t h_pin_cap = 0;
@@ -127,6 +126,7 @@ static int fail(mpc_ctx *ctx, int code, const char *fmt, ...) {
     } while (0)
 
 static void invalidate_graphs(mpc_ctx *ctx);
+static cudaError_t raise_smem_limits(const cudaDeviceProp &prop);
 
 // grow-only device buffer; a reallocation moves pointers that captured graphs hold, so it drops them
 static cudaError_t ensure(mpc_ctx *ctx, DevBuf &b, size_t bytes) {
@@ -179,6 +179,7 @@ extern "C" int mpc_create(int device, mpc_ctx **out) {
     CU(cudaGetDeviceProperties(&ctx->prop, device));
     if (ctx->prop.major < 9) return fail(ctx, MPC_E_CUDA, "device sm_%d%d lacks TMA bulk copies; built for sm_100a", ctx->prop.major, ctx->prop.minor);
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(raise_smem_limits(ctx->prop));     // once, here: the attribute cannot be changed while a graph is being captured
     for (auto &ev : ctx->ev) CU(cudaEventCreate(&ev));
     CU(ensure(ctx, ctx->res_d, sizeof(Counters) + 4096));
     CU(ensure(ctx, ctx->maxabs, sizeof(float)));
@@ -721,12 +722,6 @@ static cudaError_t launch_check_vb(mpc_ctx *ctx, const KParams &p) {
     // full evaluation never culls: one instantiation per (COUNT) is enough
     auto kern = nocull ? (count ? k_check<VA, VB, true, true, false> : k_check<VA, VB, false, true, false>)
                        : (count ? k_check<VA, VB, true, false, SEGCULL> : k_check<VA, VB, false, false, SEGCULL>);
-    const int key = VA * 1000 + VB * 10 + (count ? 1 : 0) + (nocull ? 2 : (SEGCULL ? 4 : 0));
-    if (ctx->smem > 48 * 1024 && ctx->smem_attr[key] < ctx->smem) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem);
-        if (e != cudaSuccess) return e;
-        ctx->smem_attr[key] = ctx->smem;
-    }
     kern<<<ctx->ctas, K_THREADS, ctx->smem, ctx->stream>>>(p);
     return cudaGetLastError();
 }
@@ -747,6 +742,34 @@ static cudaError_t launch_check(mpc_ctx *ctx, const KParams &p) {
     if (va == 8 && vb == 8) return launch_check_seg<8, 8>(ctx, p);
     if (va == 16 && vb == 4) return launch_check_seg<16, 4>(ctx, p);
     return launch_check_seg<16, 8>(ctx, p);
+}
+
+// every instantiation of k_check may use the whole opt-in shared memory of the device (tiles of many-vertex polygons
+// or long boundaries exceed the 48 KB default)
+template <int VA, int VB>
+static cudaError_t raise_smem_va_vb(int bytes) {
+    cudaError_t e;
+#define MPC_RAISE(...) \
+    if ((e = cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    MPC_RAISE(k_check<VA, VB, false, false, false>)
+    MPC_RAISE(k_check<VA, VB, false, false, true>)
+    MPC_RAISE(k_check<VA, VB, true, false, false>)
+    MPC_RAISE(k_check<VA, VB, true, false, true>)
+    MPC_RAISE(k_check<VA, VB, false, true, false>)
+    MPC_RAISE(k_check<VA, VB, true, true, false>)
+#undef MPC_RAISE
+    return cudaSuccess;
+}
+
+static cudaError_t raise_smem_limits(const cudaDeviceProp &prop) {
+    const int bytes = (int)prop.sharedMemPerBlockOptin;
+    cudaError_t e;
+    if ((e = raise_smem_va_vb<4, 4>(bytes)) != cudaSuccess) return e;
+    if ((e = raise_smem_va_vb<4, 8>(bytes)) != cudaSuccess) return e;
+    if ((e = raise_smem_va_vb<8, 4>(bytes)) != cudaSuccess) return e;
+    if ((e = raise_smem_va_vb<8, 8>(bytes)) != cudaSuccess) return e;
+    if ((e = raise_smem_va_vb<16, 4>(bytes)) != cudaSuccess) return e;
+    return raise_smem_va_vb<16, 8>(bytes);
 }
 
 static int launch_all(mpc_ctx *ctx, cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2) {
@@ -820,6 +843,8 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
     ctx->cap_s = std::max(32, std::min((ctx->max_seg_step + 31) / 32 * 32, 512));
     ctx->smem = 16 + 3 * GPC_MAX * 4 + (size_t)nwarps * QCAP * 4 + (size_t)nwarps * FA * 32 * 16 +
                 (size_t)ctx->cap_o * (F * 16 + 12) + (size_t)ctx->cap_s * 32;
+    if (ctx->smem > ctx->prop.sharedMemPerBlockOptin)
+        return fail(ctx, MPC_E_LIMIT, "tile of %zu bytes exceeds the device's shared memory", ctx->smem);
     // pack: QDev[B], cta_off[B+1] (one copy), explicit candidates (second copy, only when present)
     size_t bytes_q = sizeof(QDev) * (size_t)std::max(B, 1), bytes_c = (sizeof(int) * (size_t)(B + 1) + 15) / 16 * 16;
     const size_t bytes_h = 16, bytes_i = sizeof(int) * (size_t)ncand;
@@ -1002,17 +1027,12 @@ static int run_batch(mpc_ctx *ctx, uint32_t *out_mask, int mask_words, mpc_stats
     if (mask_words > 0 && !out_mask) return fail(ctx, MPC_E_ARG, "out_mask missing");
     float ms = 0.f;
     int kernels = 2, overflow = 0, rc;
-    if (ctx->smem > 48 * 1024) {          // large tiles need the opt-in attribute, which cannot be set during capture
+    rc = run_graph(ctx, &ms, stats != nullptr);
+    if (!rc && ((const Counters *)ctx->h_res)->wl_count > (unsigned)ctx->wl_cap) {
+        // refinement list overflowed: the plain path grows it and re-runs (and drops the graphs)
         rc = issue_uploads(ctx);
         if (!rc) rc = run_once(ctx, &ms, &kernels, &overflow, stats != nullptr);
-    } else {
-        rc = run_graph(ctx, &ms, stats != nullptr);
-        if (!rc && ((const Counters *)ctx->h_res)->wl_count > (unsigned)ctx->wl_cap) {
-            // refinement list overflowed: the plain path grows it and re-runs (and drops the graphs)
-            rc = issue_uploads(ctx);
-            if (!rc) rc = run_once(ctx, &ms, &kernels, &overflow, stats != nullptr);
-            overflow = 1;
-        }
+        overflow = 1;
     }
     if (rc) return rc;
     if (mask_words) memcpy(out_mask, (const char *)ctx->h_res + sizeof(Counters), sizeof(unsigned) * (size_t)mask_words);
