@@ -40,8 +40,8 @@ FLOP_PER_CHECK = 304            # rectangle x rectangle SAT, a =
 SAT_FLOP_EXECUTED = 160         # this kernel's full 4x4 test: 64 FMA (2 flop) + 24 min + 8 max
 CULL_FLOP_EXECUTED = 6          # centre-line axis per pair: 2 add + 2 fma (packed FADD2/FFMA2: two pairs per instruction)
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # no FP32 entry in MEASURED_PEAKS.json: derived from its sm_max_mhz
-NCU_DRAM_BYTES_PER_LAUNCH = 9252864    # ncu capture k (profiles/): dram__bytes_read.sum of one 64-query launch; write 23 KB
-NCU_WARP_INST_PER_LAUNCH = 129062748   # same capture: smsp__inst_executed.sum of that launch (a count, not a time)
+NCU_DRAM_BYTES_PER_LAUNCH = 6521600    # ncu capture l (profiles/): dram__bytes_read.sum of one 64-query launch; write 2 KB
+NCU_WARP_INST_PER_LAUNCH = 90259337   # same capture: smsp__inst_executed.sum of that launch (a count, not a time)
 ISSUE_PEAK = 148 * 4 * 1.965e9         # warp instructions per second: 4 schedulers per SM, one issue per clock
 METRIC = "primitive x obstacle x timestep collision checks/sec"
 WORKLOAD = ("C4 dense traffic: 4096 primitives x 256 obstacles x 50 timesteps per query (BASELINE.json configs[3])")
@@ -331,7 +331,7 @@ def main():
                         "duration of k_check. The kernel is NOT FP32-bound and is not meant to be: 80 % of the nominal "
                         "pairs are never looked at (their candidate already collides at another time step -- the "
                         "reference's early return), sub-block bounding boxes separate 17 %, the centre-line axis all "
-                        "but 0.06 % of the rest. ncu (profiles/r01k_k_check_ncu_full.csv): instruction issue 65 % of "
+                        "but 0.06 % of the rest. ncu (profiles/r01l_k_check_ncu_full.csv): instruction issue 65 % of "
                         "peak (see issue_slots), ALU pipe 43 %, FMA pipe 18 %; HBM traffic is below the algorithmic "
                         "bytes because skipped tiles are never fetched. The arithmetic rate of the full test is "
                         "full_evaluation (no culling, no exits): 57 % of the FP32 peak.",
@@ -348,7 +348,7 @@ def main():
                                        "frac": algo_tflops / FP32_PEAK_TFLOPS,
                                        "note": "SURVEY.md 8(d) definition: 304 flop x checks / time. Above 1 by "
                                                "construction: early return, sub-block boxes and the centre-line axis (6 flop) "
-                                               "decide 99.94 % of the pairs, so the algorithmic count is not executed."},
+                                               "decide 99.96 % of the pairs, so the algorithmic count is not executed."},
                 "full_evaluation": {"checks_per_s": full_checks / (full_main * 1e-3),
                                     "achieved": full_checks * SAT_FLOP_EXECUTED / (full_main * 1e-3) / 1e12,
                                     "frac": full_checks * SAT_FLOP_EXECUTED / (full_main * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
@@ -362,10 +362,10 @@ def main():
                                 "note": "the binding resource per ncu: executed warp instructions of one launch (count "
                                         "from the committed capture) / live CUDA-event duration, against 148 SM x 4 "
                                         "schedulers x sm_max_mhz"},
-                "ncu": {"source": "profiles/r01k_k_check_ncu_full.csv", "smsp__issue_active_pct": 65.4,
-                        "l1tex__data_pipe_lsu_wavefronts_pct": 38.7, "sm__inst_executed_pipe_fma_pct": 18.0,
-                        "sm__inst_executed_pipe_alu_pct": 43.0, "smsp__inst_executed": NCU_WARP_INST_PER_LAUNCH,
-                        "dram__bytes_read": NCU_DRAM_BYTES_PER_LAUNCH, "dram__bytes_write": 23296,
+                "ncu": {"source": "profiles/r01l_k_check_ncu_full.csv", "smsp__issue_active_pct": 58.2,
+                        "l1tex__data_pipe_lsu_wavefronts_pct": 32.1, "sm__inst_executed_pipe_fma_pct": 15.2,
+                        "sm__inst_executed_pipe_alu_pct": 36.5, "smsp__inst_executed": NCU_WARP_INST_PER_LAUNCH,
+                        "dram__bytes_read": NCU_DRAM_BYTES_PER_LAUNCH, "dram__bytes_write": 2048,
                         "note": "which tiles are skipped depends on scheduling: counts vary by a few percent between launches"},
                 "hbm": {"algorithmic_bytes": algo_bytes, "achieved_gbs": algo_bytes / (main_ms * 1e-3) / 1e9,
                         "peak_gbs": hbm_peak, "frac": algo_bytes / (main_ms * 1e-3) / 1e9 / hbm_peak,

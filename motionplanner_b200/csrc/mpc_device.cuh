@@ -39,7 +39,7 @@ struct KParams {
     const float4 *slib_v, *slib_n, *slib_c;    // [field][J][set_total]: copy in sorted-set order, read coalesced
     int set_total;
     const double *lib_v64;
-    const int *lib_nv, *slot_t;
+    const int *lib_nv, *slot_t, *slot_perm;      // slot_perm[l]: time slot launched at level l of the slot-major grid
     int PJ, J, lib_vmax;
     // scenes
     const float4 *ob_f;          // [F-1][ob_stride] vertex and edge-line fields, slot layout (steps 32-aligned)
@@ -567,7 +567,8 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
     // (largest q with cta_off[q] <= c; every warp finds it with warp-wide loads and votes instead of a chain of
     // dependent loads: a 32-way search per round)
     const int c_total = p.c_total;                              // CTAs per time slot (sum of the queries' chunks)
-    const int j = (int)blockIdx.x / c_total, cidx = (int)blockIdx.x - j * c_total;
+    const int level = (int)blockIdx.x / c_total, cidx = (int)blockIdx.x - level * c_total;
+    const int j = __ldg(p.slot_perm + level);
     int q = 0;
     {
         int lo = 0, hi = p.B + 1;                 // answer in [lo, hi)

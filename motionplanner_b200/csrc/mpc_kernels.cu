@@ -344,6 +344,24 @@ extern "C" int mpc_upload_library(mpc_ctx *ctx, const double *verts, const int32
     CU(ensure(ctx, ctx->lib_c, hc.size() * sizeof(float4)));
     CU(ensure(ctx, ctx->lib_v64, h64.size() * sizeof(double)));
     CU(ensure(ctx, ctx->lib_nv, hnv.size() * sizeof(int)));
+    // Order in which the time slots are launched (slot-major grid).  Any order gives the same bits; what matters is how
+    // soon candidates get decided, because decided candidates are skipped at all other slots.  Violations become more
+    // likely with time (a primitive that has left the road stays off it, traffic ahead is reached later), so the
+    // latest slots go first, interleaved with the earliest: latest, earliest, second latest, ...  Measured on the C4
+    // batch: forward 0.185 ms, reverse 0.149 ms, interleaved 0.145 ms, middle-out 0.166 ms.  MPC_SLOT_ORDER=0/1/3 select
+    // forward / reverse / middle-out for experiments.
+    {
+        std::vector<int> perm(J);
+        const char *e = getenv("MPC_SLOT_ORDER");
+        const int kind = e ? atoi(e) : 2;
+        for (int l = 0; l < J; l++) perm[l] = l;
+        if (kind == 1) std::reverse(perm.begin(), perm.end());
+        if (kind == 2)
+            for (int l = 0; l < J; l++) perm[l] = (l & 1) ? l / 2 : J - 1 - l / 2;
+        if (kind == 3)
+            std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return std::abs(2 * a - J) < std::abs(2 * b - J); });
+        slot_t.insert(slot_t.end(), perm.begin(), perm.end());
+    }
     CU(ensure(ctx, ctx->slot_t, slot_t.size() * sizeof(int)));
     CU(cudaMemcpyAsync(ctx->lib_v.p, hv.data(), hv.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->lib_n.p, hn.data(), hn.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
@@ -684,7 +702,7 @@ static KParams make_params(mpc_ctx *ctx) {
     p.lib_v = (const float4 *)ctx->lib_v.p; p.lib_n = (const float4 *)ctx->lib_n.p; p.lib_c = (const float4 *)ctx->lib_c.p;
     p.slib_v = (const float4 *)ctx->slib_v.p; p.slib_n = (const float4 *)ctx->slib_n.p; p.slib_c = (const float4 *)ctx->slib_c.p;
     p.set_total = ctx->set_total;
-    p.lib_v64 = (const double *)ctx->lib_v64.p; p.lib_nv = (const int *)ctx->lib_nv.p; p.slot_t = (const int *)ctx->slot_t.p;
+    p.lib_v64 = (const double *)ctx->lib_v64.p; p.lib_nv = (const int *)ctx->lib_nv.p; p.slot_t = (const int *)ctx->slot_t.p; p.slot_perm = p.slot_t + ctx->J;
     p.PJ = ctx->P * ctx->J; p.J = ctx->J; p.lib_vmax = ctx->lib_vmax;
     p.ob_f = (const float4 *)ctx->ob_f.p; p.ob_c = (const float *)ctx->ob_c.p; p.ob_box = (const float4 *)ctx->ob_box.p;
     p.ob_v64 = (const double *)ctx->ob_in.p; p.ob_nv = (const int *)ctx->ob_nv.p;
