@@ -29,7 +29,8 @@ struct QDev {
 
 struct Counters {
     unsigned long long pairs_nominal, refined, exact_ties, near_tangent, parity_refined, cull_tests, axis_tests;
-    unsigned wl_count, pad;
+    unsigned wl_count;
+    float tau;                   // the float32 error band the launch used (k_check block 0 reports it)
     unsigned long long box_skipped, done_skipped, pad1[6];
 };
 
@@ -587,6 +588,8 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
     const int chunk = cidx - p.cta_off[q];
     int t = Q->t0 + p.slot_t[j];
     // reference guards: ind + time <= param['steps'] and ind + time < len(space)  (lowLevelPlannerManeuverAutomaton.py:120,122)
+    if (blockIdx.x == 0 && tid == 0)       // for the statistics: the host never reads the scene's extent itself
+        p.cnt->tau = fmaxf(fmaxf(*p.maxabs_scene, *p.maxabs_query) * (1.0f / 131072.0f), 1e-7f);
     if (t > Q->step_limit || t < 0 || t >= Q->nsteps) return;
     int step = Q->step0 + t;
     // obstacles of the step: a 32-aligned slot range (padding slots are far away), `nobst` real ones

@@ -77,7 +77,6 @@ struct mpc_ctx {
     DevBuf ob_in, ob_f, ob_nv, step_obst_off, step_seg_begin, step_seg_end, scene_step_off_d, origins_d, sg_64, sg_f,
         sg_box, seg_scene, maxabs;
     int sg_stride = 32;
-    float maxabs_scene = 0.f;
     DevBuf sg_raw, sg_jobs;       // large scene sets: caller's segments as they are + the range table, sorted on the device
     DevBuf meta;                  // one allocation behind the small per-scene arrays (views below), one H2D copy
     void *h_meta = nullptr;
@@ -677,11 +676,8 @@ static int set_scenes_impl(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_
         CU(cudaGetLastError());
     }
     lap("enqueue copies+kernels");
-    float m = 0.f;
-    CU(cudaMemcpyAsync(&m, ctx->maxabs.p, sizeof(float), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     lap("device sync");      // host buffers (incl. the local staging vectors) may be reused after return
-    ctx->maxabs_scene = m;
     ctx->nscenes = nscenes; ctx->nsteps = nsteps; ctx->nobst = nobst; ctx->nseg = nslots; ctx->sg_stride = sg_stride;
     ctx->ob_stride = ob_stride;
     ctx->ob_vmax = VB; ctx->VB = VB; ctx->max_obst_step = max_o; ctx->max_seg_step = max_s;
@@ -960,7 +956,7 @@ static void fill_stats(mpc_ctx *ctx, mpc_stats *st, float ms, int kernels, int o
     st->ms_device = ms;
     st->ctas = ctx->ctas;
     st->kernels = kernels;
-    st->tau = std::max(std::max(ctx->maxabs_scene, ctx->maxabs_query) / 131072.0f, 1e-7f);
+    st->tau = c.tau;
 }
 
 static cudaError_t ensure_result_host(mpc_ctx *ctx, size_t bytes) {
