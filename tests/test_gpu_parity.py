@@ -481,3 +481,34 @@ def test_randomised_batch_shapes_against_oracle(eng, seed):
         want, ost = pb.check(q, cand, omode | orc.MODE_NO_EARLY_EXIT)
         assert np.array_equal(got, want), (P, T, slots, B, mode)
         assert st["pairs_nominal"] == ost["pairs_nominal"], (P, T, slots, B, mode)
+
+
+def test_compaction_with_general_polygons(eng):
+    """the compaction path in the 8-vertex instantiations: 200 queries x 1024 candidates (32 groups per CTA) of an
+    adversarial library of general convex polygons against near-touching general obstacles"""
+    lib, sc, org, q = W.adversarial_problem(21, P=2048, J=8, nsteps=8, max_obst=12, lib_verts=8, obst_verts=8, nqueries=200,
+                                            with_region=False)
+    assert (lib["nv"] > 0).mean() < 1.0                    # the generator leaves holes: no compaction with this library
+    stage(eng, lib, sc, org)
+    pb = orc.Problem(lib, sc)
+    got, st = eng.query(q, None, MODE_PLANNER)
+    want, ost = pb.check(q, None, orc.MODE_NO_EARLY_EXIT)
+    assert np.array_equal(got, want) and st["pairs_nominal"] == ost["pairs_nominal"]
+    # fill the holes (copy the previous occupancy): now every slot is occupied and the compaction applies
+    lib2 = dict(lib, verts=lib["verts"].copy(), nv=lib["nv"].copy())
+    for p_, j_ in zip(*np.nonzero(lib2["nv"] == 0)):
+        src = np.nonzero(lib["nv"][p_] > 0)[0]
+        k = src[0] if len(src) else None
+        if k is None:
+            lib2["verts"][p_, j_, :3] = [[0, 0], [1, 0], [0, 1]]
+            lib2["nv"][p_, j_] = 3
+        else:
+            lib2["verts"][p_, j_] = lib["verts"][p_, k]
+            lib2["nv"][p_, j_] = lib["nv"][p_, k]
+    stage(eng, lib2, sc, org)
+    for mode, omode in ((MODE_PLANNER, 0), (MODE_VALIDATOR, orc.MODE_STRICT)):
+        got, st = eng.query(q, None, mode)
+        want, ost = orc.Problem(lib2, sc).check(q, None, omode | orc.MODE_NO_EARLY_EXIT)
+        assert np.array_equal(got, want) and st["pairs_nominal"] == ost["pairs_nominal"]
+    assert st["ctas"] > 148 * 4
+    assert 0.02 < got.mean() < 0.98
