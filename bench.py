@@ -342,6 +342,7 @@ def main():
                              "pairs_separated_by_block_box": st_cnt["box_skipped"],
                              "pairs_skipped_after_collision_at_another_step": st_cnt["done_skipped"],
                              "pairs_nominal": st_cnt["pairs_nominal"], "flop": exec_flop,
+                             "pairs_looked_at_frac": (st_cnt["cull_tests"] + st_cnt["box_skipped"]) / max(st_cnt["pairs_nominal"], 1),
                              "note": "instrumented launch of the same batch; which tiles are skipped depends on "
                                      "scheduling, the decisions do not"},
                 "algorithmic_survey": {"flop_per_check": FLOP_PER_CHECK, "achieved": algo_tflops,

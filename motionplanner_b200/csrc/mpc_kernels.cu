@@ -1056,9 +1056,18 @@ static int run_batch(mpc_ctx *ctx, uint32_t *out_mask, int mask_words, mpc_stats
 
 extern "C" int mpc_query(mpc_ctx *ctx, int B, const mpc_query_desc *queries, const int32_t *cand_idx, int ncand,
                          unsigned mode, uint32_t *out_mask, int mask_words, mpc_stats *stats) {
+    static const bool dbg_t = getenv("MPC_DEBUG_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     int rc = prepare_host(ctx, B, queries, cand_idx, ncand, mode, false);
     if (rc) return rc;
-    return run_batch(ctx, out_mask, mask_words, stats);
+    const auto t1 = std::chrono::steady_clock::now();
+    rc = run_batch(ctx, out_mask, mask_words, stats);
+    if (dbg_t) {
+        const auto t2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[mpc query] pack %.1f us, launch + wait + copy back %.1f us\n",
+                std::chrono::duration<double, std::micro>(t1 - t0).count(), std::chrono::duration<double, std::micro>(t2 - t1).count());
+    }
+    return rc;
 }
 
 extern "C" int mpc_run_prepared(mpc_ctx *ctx, int iters, int flush_l2, float *ms_total, float *ms_main, mpc_stats *stats) {
