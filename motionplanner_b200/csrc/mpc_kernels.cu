@@ -87,6 +87,7 @@ struct mpc_ctx {
     size_t qpack_cta_off = 0, qpack_hdr_off = 0, up_bytes = 0, up_cand_bytes = 0, up_cand_src = 0;
     unsigned long long generation = 0;          // bumped whenever a pointer a captured graph holds may have changed
     std::map<std::vector<long long>, cudaGraphExec_t> graphs;
+    std::map<std::vector<long long>, cudaGraphExec_t> scene_graphs;      // staging of small scenes from pinned arrays
     void *h_res = nullptr;
     size_t h_res_cap = 0;
     int wl_cap = 0;
@@ -143,6 +144,8 @@ static cudaError_t ensure(mpc_ctx *ctx, DevBuf &b, size_t bytes) {
 static void invalidate_graphs(mpc_ctx *ctx) {
     for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
     ctx->graphs.clear();
+    for (auto &kv : ctx->scene_graphs) cudaGraphExecDestroy(kv.second);
+    ctx->scene_graphs.clear();
     ctx->generation++;
 }
 
@@ -206,6 +209,7 @@ extern "C" void mpc_destroy(mpc_ctx *ctx) {
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+    for (auto &kv : ctx->scene_graphs) cudaGraphExecDestroy(kv.second);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
@@ -481,16 +485,33 @@ static int set_scenes_impl(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_
     if (nobst > 0 && (Vo < 3 || Vo > MPC_MAX_OBST_VERTS)) return fail(ctx, MPC_E_LIMIT, "Vo=%d outside 3..%d", Vo, MPC_MAX_OBST_VERTS);
     if (nseg > 0 && !segs) return fail(ctx, MPC_E_ARG, "segment array missing");
     cudaStream_t st = ctx->stream;
+    // large segment sets are sorted on the device
+    const bool seg_dev_wanted = nseg >= 8192;
+    // A small scene in page-locked arrays (a planner re-staging its prediction every cycle) is staged by replaying a
+    // captured graph: one driver call instead of eight.  Everything the nodes hold is in the key below.
+    auto pinned = [](const void *ptr) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    static const bool no_scene_graph = getenv("MPC_NO_SCENE_GRAPH") != nullptr;
+    const bool use_graph = !no_scene_graph && !seg_dev_wanted && (size_t)nobst * Vo * 2 * sizeof(double) <= ((size_t)4 << 20) &&
+                           (nobst == 0 || (pinned(obst) && pinned(obst_nv)));
     // the bulk of the bytes first: the caller's obstacle rows travel as they are (one contiguous DMA, read by the staging
     // kernels with stride Vo) while the host validates and sorts the rest
     CU(ensure(ctx, ctx->ob_src, (size_t)std::max(nobst, 1) * Vo * 2 * sizeof(double)));
     CU(ensure(ctx, ctx->ob_src_nv, (size_t)std::max(nobst, 1) * sizeof(int)));
-    if (nobst) {
-        CU(cudaMemcpyAsync(ctx->ob_src.p, obst, (size_t)nobst * Vo * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(ctx->ob_src_nv.p, obst_nv, (size_t)nobst * sizeof(int), cudaMemcpyHostToDevice, st));
+    auto copy_obstacles = [&]() -> int {
+        if (nobst) {
+            CU(cudaMemcpyAsync(ctx->ob_src.p, obst, (size_t)nobst * Vo * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(ctx->ob_src_nv.p, obst_nv, (size_t)nobst * sizeof(int), cudaMemcpyHostToDevice, st));
+        }
+        return MPC_OK;
+    };
+    if (!use_graph) {
+        const int rc = copy_obstacles();
+        if (rc) return rc;
     }
-    // large segment sets are sorted on the device: their bytes start travelling now as well
-    const bool seg_dev_wanted = nseg >= 8192;
     if (seg_dev_wanted) {
         CU(ensure(ctx, ctx->sg_raw, (size_t)nseg * 4 * sizeof(double)));
         CU(cudaMemcpyAsync(ctx->sg_raw.p, segs, (size_t)nseg * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -561,6 +582,8 @@ static int set_scenes_impl(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_
     CU(ensure(ctx, ctx->sg_box, (size_t)(sg_stride / 8 + 1) * sizeof(float4)));
     lap("validate + ensure");
     // the small per-scene arrays travel as one packed block (one driver call instead of nine)
+    size_t meta_bytes = 0, m_org = 0, m_sg = 0, m_sso = 0, m_ss = 0;
+    bool use_seg_dev = false;
     {
         const size_t n_org = (size_t)nscenes * 2 * sizeof(double), n_sg = (size_t)sg_stride * 4 * sizeof(double);
         const size_t n_sso = (size_t)(nscenes + 1) * 4, n_st1 = (size_t)(nsteps + 1) * 4, n_st = (size_t)std::max(nsteps, 1) * 4;
@@ -625,55 +648,92 @@ static int set_scenes_impl(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_
             memcpy(h + o_se, dev_end.data(), (size_t)nsteps * 4);
         }
         lap("pack meta (pass 2)");
-        if (!seg_dev) {
-            CU(cudaMemcpyAsync(d, h, off, cudaMemcpyHostToDevice, st));
-        } else {
-            // everything but the two segment arrays, which k_order_segs writes from the raw copy
-            CU(cudaMemcpyAsync(d + o_org, h + o_org, o_sg - o_org, cudaMemcpyHostToDevice, st));
-            CU(cudaMemcpyAsync(d + o_sso, h + o_sso, o_ss - o_sso, cudaMemcpyHostToDevice, st));
-            const int njobs = (int)jobs.size();
-            CU(ensure(ctx, ctx->sg_jobs, sizeof(int4) * (size_t)std::max(njobs, 1)));
-            int4 *hj = (int4 *)(h + o_sg);                     // the unused segment area of the pinned block as staging
-            for (int jb = 0; jb < njobs; jb++) hj[jb] = make_int4(jobs[jb].b, jobs[jb].e, jobs[jb].scene, jobs[jb].start);
-            CU(cudaMemcpyAsync(ctx->sg_jobs.p, hj, sizeof(int4) * (size_t)njobs, cudaMemcpyHostToDevice, st));
-            if (njobs) {
-                k_order_segs<<<njobs, 256, 0, st>>>((const int4 *)ctx->sg_jobs.p, (const double *)ctx->sg_raw.p,
-                                                   (double *)(d + o_sg), (int *)(d + o_ss));
-                CU(cudaGetLastError());
-            }
-        }
         ctx->origins_d.p = d + o_org; ctx->sg_64.p = d + o_sg; ctx->scene_step_off_d.p = d + o_sso;
         ctx->step_obst_off.p = d + o_slot; ctx->ob_src_off.p = d + o_src; ctx->step_obst_cnt.p = d + o_cnt;
         ctx->step_seg_begin.p = d + o_sb; ctx->step_seg_end.p = d + o_se; ctx->seg_scene.p = d + o_ss;
         // captured graphs hold these addresses: a different layout is a different graph
         ctx->meta_sig = (long long)(o_sg * 1315423911ull ^ o_sso * 2654435761ull ^ o_slot * 40503ull ^ o_ss * 97ull ^ off);
+        meta_bytes = off; m_org = o_org; m_sg = o_sg; m_sso = o_sso; m_ss = o_ss;
+        use_seg_dev = seg_dev;
     }
-    CU(cudaMemsetAsync(ctx->maxabs.p, 0, sizeof(float), st));
-    if (nobst) {
-        int blocks = (noslots + 127) / 128;
-        if (VB == 4) {
-            k_order_obst<4><<<nsteps, 256, 0, st>>>((const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_src_off.p,
-                                                    (const int *)ctx->step_obst_off.p, (const int *)ctx->scene_step_off_d.p, nscenes,
-                                                    (const double *)ctx->origins_d.p, (int *)ctx->ob_order.p, Vo);
-            k_stage_obst<4><<<blocks, 128, 0, st>>>(noslots, (const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_order.p,
-                                                   (const int *)ctx->step_obst_off.p, nsteps, (const int *)ctx->scene_step_off_d.p, nscenes,
-                                                   (const double *)ctx->origins_d.p, (float4 *)ctx->ob_f.p, (float *)ctx->ob_c.p, (float4 *)ctx->ob_box.p,
-                                                   (double *)ctx->ob_in.p, (int *)ctx->ob_nv.p, ob_stride, (float *)ctx->maxabs.p, Vo);
+    // everything that goes to the stream after the host-side passes
+    auto enqueue_rest = [&]() -> int {
+        char *h = (char *)ctx->h_meta, *d = (char *)ctx->meta.p;
+        if (!use_seg_dev) {
+            CU(cudaMemcpyAsync(d, h, meta_bytes, cudaMemcpyHostToDevice, st));
         } else {
-            k_order_obst<8><<<nsteps, 256, 0, st>>>((const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_src_off.p,
-                                                    (const int *)ctx->step_obst_off.p, (const int *)ctx->scene_step_off_d.p, nscenes,
-                                                    (const double *)ctx->origins_d.p, (int *)ctx->ob_order.p, Vo);
-            k_stage_obst<8><<<blocks, 128, 0, st>>>(noslots, (const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_order.p,
-                                                   (const int *)ctx->step_obst_off.p, nsteps, (const int *)ctx->scene_step_off_d.p, nscenes,
-                                                   (const double *)ctx->origins_d.p, (float4 *)ctx->ob_f.p, (float *)ctx->ob_c.p, (float4 *)ctx->ob_box.p,
-                                                   (double *)ctx->ob_in.p, (int *)ctx->ob_nv.p, ob_stride, (float *)ctx->maxabs.p, Vo);
+            // everything but the two segment arrays, which k_order_segs writes from the raw copy
+            CU(cudaMemcpyAsync(d + m_org, h + m_org, m_sg - m_org, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(d + m_sso, h + m_sso, m_ss - m_sso, cudaMemcpyHostToDevice, st));
+            const int njobs = (int)jobs.size();
+            CU(ensure(ctx, ctx->sg_jobs, sizeof(int4) * (size_t)std::max(njobs, 1)));
+            int4 *hj = (int4 *)(h + m_sg);                     // the unused segment area of the pinned block as staging
+            for (int jb = 0; jb < njobs; jb++) hj[jb] = make_int4(jobs[jb].b, jobs[jb].e, jobs[jb].scene, jobs[jb].start);
+            CU(cudaMemcpyAsync(ctx->sg_jobs.p, hj, sizeof(int4) * (size_t)njobs, cudaMemcpyHostToDevice, st));
+            if (njobs) {
+                k_order_segs<<<njobs, 256, 0, st>>>((const int4 *)ctx->sg_jobs.p, (const double *)ctx->sg_raw.p,
+                                                   (double *)(d + m_sg), (int *)(d + m_ss));
+                CU(cudaGetLastError());
+            }
         }
-        CU(cudaGetLastError());
-    }
-    if (nslots) {
-        k_stage_segs<<<(nslots + 127) / 128, 128, 0, st>>>(nslots, (const double *)ctx->sg_64.p, (const int *)ctx->seg_scene.p, (const double *)ctx->origins_d.p,
-                                                         (float4 *)ctx->sg_f.p, sg_stride, (float4 *)ctx->sg_box.p, (float *)ctx->maxabs.p);
-        CU(cudaGetLastError());
+        CU(cudaMemsetAsync(ctx->maxabs.p, 0, sizeof(float), st));
+        if (nobst) {
+            int blocks = (noslots + 127) / 128;
+            if (VB == 4) {
+                k_order_obst<4><<<nsteps, 256, 0, st>>>((const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_src_off.p,
+                                                        (const int *)ctx->step_obst_off.p, (const int *)ctx->scene_step_off_d.p, nscenes,
+                                                        (const double *)ctx->origins_d.p, (int *)ctx->ob_order.p, Vo);
+                k_stage_obst<4><<<blocks, 128, 0, st>>>(noslots, (const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_order.p,
+                                                       (const int *)ctx->step_obst_off.p, nsteps, (const int *)ctx->scene_step_off_d.p, nscenes,
+                                                       (const double *)ctx->origins_d.p, (float4 *)ctx->ob_f.p, (float *)ctx->ob_c.p, (float4 *)ctx->ob_box.p,
+                                                       (double *)ctx->ob_in.p, (int *)ctx->ob_nv.p, ob_stride, (float *)ctx->maxabs.p, Vo);
+            } else {
+                k_order_obst<8><<<nsteps, 256, 0, st>>>((const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_src_off.p,
+                                                        (const int *)ctx->step_obst_off.p, (const int *)ctx->scene_step_off_d.p, nscenes,
+                                                        (const double *)ctx->origins_d.p, (int *)ctx->ob_order.p, Vo);
+                k_stage_obst<8><<<blocks, 128, 0, st>>>(noslots, (const double *)ctx->ob_src.p, (const int *)ctx->ob_src_nv.p, (const int *)ctx->ob_order.p,
+                                                       (const int *)ctx->step_obst_off.p, nsteps, (const int *)ctx->scene_step_off_d.p, nscenes,
+                                                       (const double *)ctx->origins_d.p, (float4 *)ctx->ob_f.p, (float *)ctx->ob_c.p, (float4 *)ctx->ob_box.p,
+                                                       (double *)ctx->ob_in.p, (int *)ctx->ob_nv.p, ob_stride, (float *)ctx->maxabs.p, Vo);
+            }
+            CU(cudaGetLastError());
+        }
+        if (nslots) {
+            k_stage_segs<<<(nslots + 127) / 128, 128, 0, st>>>(nslots, (const double *)ctx->sg_64.p, (const int *)ctx->seg_scene.p, (const double *)ctx->origins_d.p,
+                                                             (float4 *)ctx->sg_f.p, sg_stride, (float4 *)ctx->sg_box.p, (float *)ctx->maxabs.p);
+            CU(cudaGetLastError());
+        }
+        return MPC_OK;
+    };
+    if (!use_graph) {
+        const int rc = enqueue_rest();
+        if (rc) return rc;
+    } else {
+        const std::vector<long long> key = {(long long)(size_t)obst, (long long)(size_t)obst_nv, nobst, Vo, VB, nsteps, nscenes, noslots, nslots,
+                                            (long long)meta_bytes, ctx->meta_sig, ob_stride, sg_stride, (long long)ctx->generation,
+                                            (long long)(size_t)ctx->h_meta};
+        auto it = ctx->scene_graphs.find(key);
+        if (it == ctx->scene_graphs.end()) {
+            if (ctx->scene_graphs.size() > 64) {
+                for (auto &kv : ctx->scene_graphs) cudaGraphExecDestroy(kv.second);
+                ctx->scene_graphs.clear();
+            }
+            cudaGraph_t graph = nullptr;
+            CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            int rc = copy_obstacles();
+            if (!rc) rc = enqueue_rest();
+            const cudaError_t e2 = cudaStreamEndCapture(st, &graph);
+            if (rc || e2 != cudaSuccess) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc ? rc : fail(ctx, MPC_E_CUDA, "scene graph capture failed: %s", cudaGetErrorString(e2));
+            }
+            cudaGraphExec_t exec = nullptr;
+            const cudaError_t e3 = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e3 != cudaSuccess) return fail(ctx, MPC_E_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e3));
+            it = ctx->scene_graphs.emplace(key, exec).first;
+        }
+        CU(cudaGraphLaunch(it->second, st));
     }
     lap("enqueue copies+kernels");
     CU(cudaStreamSynchronize(st));
