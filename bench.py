@@ -178,6 +178,8 @@ def main():
     ap.add_argument("--queries", type=int, default=64,
                     help="queries (ego poses) per step; default = the 64 jittered poses SURVEY.md 8(d) defines for C4")
     ap.add_argument("--ref-queries", type=int, default=2, help="queries per step of the CPU reference arm (bounded sample)")
+    ap.add_argument("--lanes", type=int, default=3,
+                    help="contexts per GPU for the end-to-end figure (1 = one context, strictly serial steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -273,7 +275,27 @@ def main():
         set_scene()
         mask, _ = eng.query_mask(queries, None, MODE_PLANNER)
     barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_serial_s = time.perf_counter() - t0
+    # the same steps dealt to `--lanes` contexts on this GPU, one host thread each (motionplanner_b200/lanes.py): every
+    # step still copies its scene and queries host -> device and its result bits back inside the timed region; the
+    # copies and staging kernels of one lane overlap k_check of the other
+    e2e_s, e2e_lanes = e2e_serial_s, 1
+    if args.lanes > 1:
+        from motionplanner_b200.lanes import CollisionLanes
+        pool = CollisionLanes(local, lanes=args.lanes)
+        pool.upload_library(lib["verts"], lib["nv"], lib["tidx"], lib["set_off"], lib["set_idx"])
+        cycle = (dict(scene, origins=origins), queries)
+        pool.run_cycles([cycle] * (args.lanes * args.warmup), MODE_PLANNER)
+        barrier()
+        t0 = time.perf_counter()
+        res = pool.run_cycles([cycle] * args.steps, MODE_PLANNER)
+        barrier()
+        e2e_lanes_s = time.perf_counter() - t0
+        if not all(np.array_equal(r[0], mask) for r in res[-args.lanes:]):
+            raise SystemExit("bench.py: lanes and single context disagree")
+        pool.close()
+        if e2e_lanes_s < e2e_serial_s:
+            e2e_s, e2e_lanes = e2e_lanes_s, args.lanes
     # planning-step latency: one query (B=1) against an already staged scene, host doubles in -> bitmask out
     lat = []
     for _ in range(60):
@@ -283,14 +305,14 @@ def main():
     lat_p50 = float(np.median(lat[10:]))
 
     # ---- reduce over ranks (max time), gather the result bitmasks -----------------------------------------------------
-    times = torch.tensor([dev_s, e2e_s, wall], dtype=torch.float64, device="cuda")
+    times = torch.tensor([dev_s, e2e_s, wall, e2e_serial_s], dtype=torch.float64, device="cuda")
     nfree = torch.tensor([float(len(collide) - int(collide.sum()))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         masks = [torch.empty(len(mask), dtype=torch.int32, device="cuda") for _ in range(world)] if rank == 0 else None
         dist.gather(torch.from_numpy(mask.view(np.int32)).cuda(), masks, dst=0)      # only result bitmasks travel
         dist.all_reduce(nfree)
-    dev_s, e2e_s, wall = [float(x) for x in times.cpu()]
+    dev_s, e2e_s, wall, e2e_serial_s = [float(x) for x in times.cpu()]
 
     if rank == 0:
         value = world * args.steps * checks_step / dev_s
@@ -317,8 +339,13 @@ def main():
             "e2e": {"value": world * args.steps * checks_step / e2e_s, "unit": "checks/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "lanes": e2e_lanes,
                     "what": "CollisionEngine.set_scenes + query_mask (mpc_set_scenes + mpc_query) from pinned host "
-                            "numpy buffers, every step"},
+                            "numpy buffers, every step" + ("" if e2e_lanes == 1 else "; steps dealt round-robin to %d "
+                            "contexts on the GPU, one host thread each (CollisionLanes.run_cycles), so one step's "
+                            "copies overlap another's k_check" % e2e_lanes),
+                    "single_context": {"value": world * args.steps * checks_step / e2e_serial_s,
+                                       "ms_per_step": 1e3 * e2e_serial_s / args.steps}},
             "gpu_launches": int(args.steps * 3),
             "gpu_launches_what": "per timed step: k_fill_u32 (L2 flush, outside the event bracket), k_check, k_refine",
             "clocks": clocks,

@@ -512,3 +512,34 @@ def test_compaction_with_general_polygons(eng):
         assert np.array_equal(got, want) and st["pairs_nominal"] == ost["pairs_nominal"]
     assert st["ctas"] > 148 * 4
     assert 0.02 < got.mean() < 0.98
+
+
+def test_lanes_match_single_context(eng):
+    """independent cycles (scene + queries) dealt to several contexts on one GPU, one host thread each: the staging of
+    one lane overlaps the check of another; every cycle's bits equal the oracle's and the single-context result"""
+    from motionplanner_b200.engine import unpack_mask
+    from motionplanner_b200.lanes import CollisionLanes
+    parts = [W.adversarial_problem(700 + i, P=96, nsteps=4 + (i % 3), offset=(50.0 * i, 20.0 * i)) for i in range(7)]
+    lib = parts[0][0]
+    lanes = CollisionLanes(0, lanes=3)
+    try:
+        lanes.upload_library(lib["verts"], lib["nv"], lib["tidx"], lib.get("set_off"), lib.get("set_idx"))
+        cycles = [(dict(sc, origins=org), q) for _, sc, org, q in parts]
+        for rep in range(3):                                  # repeated: lanes reuse their staged buffers and graphs
+            res = lanes.run_cycles(cycles, MODE_PLANNER)
+            for (_, sc, org, q), (mask, st) in zip(parts, res):
+                want, _ = orc.Problem(lib, sc).check(q, None, orc.MODE_NO_EARLY_EXIT)
+                assert np.array_equal(unpack_mask(mask, q), want)
+        for (_, sc, org, q), (mask, _) in zip(parts, res):
+            stage(eng, lib, sc, org)
+            single, _ = eng.query(q, None, MODE_PLANNER)
+            assert np.array_equal(unpack_mask(mask, q), single)
+        # a failing cycle stops the lanes and surfaces as the same exception a single context raises
+        bad = dict(cycles[2][0])
+        bad["obst_nv"] = np.full_like(bad["obst_nv"], 99)
+        with pytest.raises(MpcError):
+            lanes.run_cycles(cycles[:2] + [(bad, cycles[2][1])] + cycles[3:], MODE_PLANNER)
+        res2 = lanes.run_cycles(cycles, MODE_PLANNER)         # still usable afterwards
+        assert all(np.array_equal(a[0], b[0]) for a, b in zip(res, res2))
+    finally:
+        lanes.close()
