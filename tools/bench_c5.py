@@ -60,6 +60,8 @@ def main():
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--check', action='store_true', help='compare rank 0 block with the CPU oracle')
     ap.add_argument('--pageable', action='store_true', help='keep the host arrays in pageable memory')
+    ap.add_argument('--lanes', type=int, default=3, help='contexts per GPU for the second end-to-end figure: the rank\'s '
+                    'block is cut into this many sub-blocks, staged and checked concurrently (CollisionLanes)')
     args = ap.parse_args()
     rank, local, world = (int(os.environ.get(k, d)) for k, d in (('RANK', 0), ('LOCAL_RANK', 0), ('WORLD_SIZE', 1)))
     import torch
@@ -110,7 +112,30 @@ def main():
     torch.cuda.synchronize()
     e2e = (time.perf_counter() - t0) / args.iters
     t_stage /= args.iters
-    times = torch.tensor([float(np.mean(ms_total)) * 1e-3, e2e], dtype=torch.float64, device='cuda')
+    # the same block cut into sub-blocks, one per lane: copies / host passes of one overlap the kernels of another
+    e2e_lanes = float('nan')
+    if args.lanes > 1 and not args.pageable:
+        from motionplanner_b200.lanes import CollisionLanes
+        pool = CollisionLanes(local, lanes=args.lanes)
+        pool.upload_library(lay['verts'], lay['nv'], lay['tidx'], lay['set_off'], lay['set_idx'])
+        sub = block_bounds(int(b[rank + 1] - b[rank]), args.lanes) + int(b[rank])
+        cycles = []
+        for k in range(args.lanes):
+            _, sc_k, q_k, _ = build(MA, golden, args.queries, 3, args.full_library, int(sub[k]), int(sub[k + 1]))
+            cycles.append(({n: pool.pinned_like(v) for n, v in sc_k.arrays().items()}, pool.pinned_like(q_k)))
+        pool.run_cycles(cycles * 2, 0, cand)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = pool.run_cycles(cycles * args.iters, 0, cand)
+        torch.cuda.synchronize()
+        e2e_lanes = (time.perf_counter() - t0) / args.iters
+        got = np.concatenate([unpack_mask(m, c[1]) for (m, _), c in zip(res[-args.lanes:], cycles)])
+        if not np.array_equal(got, bits):
+            raise SystemExit('bench_c5: sub-blocks through lanes disagree with the single batch')
+        pool.close()
+    times = torch.tensor([float(np.mean(ms_total)) * 1e-3, e2e, e2e_lanes], dtype=torch.float64, device='cuda')
     tot = torch.tensor([float(st['pairs_nominal']), float(bits.sum()), float(len(bits)), float(st['refined_fp64']),
                         float(st['near_tangent'])], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -125,11 +150,12 @@ def main():
         want, _ = orc.Problem(lib, arrays).check(q, cand, orc.MODE_NO_EARLY_EXIT)
         disagreements = int((want != bits).sum())
     if rank == 0:
-        dev_s, e2e_s = [float(v) for v in times.cpu()]
+        dev_s, e2e_s, e2e_lanes_s = [float(v) for v in times.cpu()]
         pairs, coll, ncand, refined, near = [float(v) for v in tot.cpu()]
         line = {"workload": "C5: %d scenario-shaped queries (seed 3), %s" % (args.queries, "full library 13702" if args.full_library else "velocity bucket <=195 candidates"),
                 "n_gpus": world, "queries_per_s_device": args.queries / dev_s, "pair_checks_per_s_device": pairs / dev_s,
                 "queries_per_s_e2e": args.queries / e2e_s, "ms_device": 1e3 * dev_s, "ms_e2e": 1e3 * e2e_s, "ms_stage_scenes_rank0": 1e3 * t_stage,
+                "lanes": args.lanes, "ms_e2e_lanes": 1e3 * e2e_lanes_s, "queries_per_s_e2e_lanes": args.queries / e2e_lanes_s,
                 "pairs_nominal": pairs, "candidates": ncand, "colliding": coll, "refined_fp64": refined,
                 "near_tangent_lt_1e-9": near, "disagreements_vs_oracle_rank0": disagreements,
                 "h2d_bytes": int(sum(v.nbytes for v in arrays.values()) + q.nbytes)}
