@@ -280,6 +280,8 @@ def main():
     # step still copies its scene and queries host -> device and its result bits back inside the timed region; the
     # copies and staging kernels of one lane overlap k_check of the other
     e2e_s, e2e_lanes = e2e_serial_s, 1
+    # every lane is a host thread that waits on its stream: no more lanes than this rank's share of the host cores
+    args.lanes = max(1, min(args.lanes, len(os.sched_getaffinity(0)) // world))
     if args.lanes > 1:
         from motionplanner_b200.lanes import CollisionLanes
         pool = CollisionLanes(local, lanes=args.lanes)
