@@ -214,3 +214,75 @@ def test_interval_occupancies_use_two_consecutive_free_spaces():
                         collide = True
             assert bool(bits[i]) == collide, (t0, i)
         assert 0 < bits.sum() < len(bits)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# whole planner runs on scenarios of the reference's own unit test (unitTests/unitTest.py:35-64: plan, then the plan
+# must pass collisionChecker), from the pickled crlite fixtures (tools/make_golden.py unit) -- no /root/reference needed
+# ---------------------------------------------------------------------------------------------------------------------
+UNIT_FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'unit_scenarios.pkl.gz')
+# (scenario, bound on popped nodes, plan expected): the stand-alone planner (no decision module) solves the two ZAM
+# scenarios; on the urban one the bounded search must fail identically on both backends
+UNIT_RUNS = [("ZAM_Zip-1_19_T-1", 20000, True), ("ZAM_Tutorial-1_1_T-1", 20000, True), ("BEL_Zaventem-4_1_T-1", 1500, False)]
+
+
+def unit_scenario(name):
+    import gzip
+    import pickle
+    with gzip.open(UNIT_FIXTURE) as f:
+        return pickle.loads(f.read())[name]
+
+
+def plan_standalone(MA, name, max_nodes, backend):
+    from motionplanner_b200.src.maneuverAutomatonPlannerStandalone import maneuverAutomatonPlannerStandalone
+    scenario, pps = unit_scenario(name)
+    param = vehicleParameter()
+    x, u, _ = maneuverAutomatonPlannerStandalone(scenario, pps, param, MA, backend=backend, max_nodes=max_nodes)
+    return scenario, param, x, u
+
+
+def test_unit_scenario_fixture_plans_on_cpu(MA):
+    from motionplanner_b200.auxiliary import collisionChecker as CC
+    be = OracleBackend()
+    scenario, param, x, u = plan_standalone(MA, "ZAM_Zip-1_19_T-1", 20000, be)
+    assert x is not None and x.shape == (4, 85) and u.shape == (2, 84)
+    flags, _ = CC.collision_flags(scenario, x, param, engine=OracleBackend())
+    assert not flags.any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,max_nodes,expect_plan", UNIT_RUNS, ids=[r[0] for r in UNIT_RUNS])
+def test_reference_unit_test_scenarios_on_gpu(MA, name, max_nodes, expect_plan):
+    """the search driven by the device's bits is the search driven by the oracle's bits -- same number of batched
+    queries, same bits in every one of them, same plan -- and the plan passes ``collisionChecker(scenario, x, param)``
+    (the drop-in validator, all steps in one device query), as the reference's unit test demands"""
+    from motionplanner_b200.auxiliary.collisionChecker import collisionChecker
+    from motionplanner_b200.engine import CollisionEngine
+
+    class Logged(CollisionEngine):
+        def query_fast(self, queries, mode=0, want_stats=False):
+            mask, st = super().query_fast(queries, mode, want_stats)
+            self.bits.append(mask.copy())
+            return mask, st
+
+        def query(self, queries, cand_idx=None, mode=0):
+            bits, st = super().query(queries, cand_idx, mode)
+            self.bits.append(np.packbits(bits, bitorder='little'))
+            return bits, st
+
+    cpu = OracleBackend()
+    _, _, x0, u0 = plan_standalone(MA, name, max_nodes, cpu)
+    eng = Logged(0)
+    eng.bits = []
+    try:
+        scenario, param, x1, u1 = plan_standalone(MA, name, max_nodes, eng)
+    finally:
+        eng.close()
+    assert (x0 is not None) == (x1 is not None) == expect_plan
+    assert len(eng.bits) == len(cpu.log) > 10
+    for got, (_, _, _, want) in zip(eng.bits, cpu.log):
+        got = np.unpackbits(np.asarray(got).view(np.uint8), bitorder='little')[:len(want)]
+        assert np.array_equal(got, want)
+    if expect_plan:
+        assert np.array_equal(x0, x1) and np.array_equal(u0, u1)
+        assert collisionChecker(scenario, x1, param) is True

@@ -8,10 +8,16 @@ container, with this package's own reader (motionplanner_b200.crlite) and road-b
                 boundary segments of the road (all lanelets: validator; same-direction lanelets reachable from the
                 start: stand-alone planner), the convex obstacle pieces of every time step in float64.
 
+Also writes tests/golden/unit_scenarios.pkl.gz: three of the scenarios the reference's own unit test plans on
+(unitTests/unitTest.py:35-38), parsed by this package's reader and pickled as crlite objects, so that the whole planner
+(not only single queries) can run on the GPU box.
+
 Run from the repository root:  python tools/make_golden.py
 """
 import glob
+import gzip
 import os
+import pickle
 import sys
 
 import numpy as np
@@ -63,5 +69,19 @@ def main(src='/root/reference/scenarios', dst=os.path.join(ROOT, 'tests', 'golde
     print('wrote', dst, os.path.getsize(dst) / 1e6, 'MB')
 
 
+UNIT_SCENARIOS = ("ZAM_Zip-1_19_T-1", "ZAM_Tutorial-1_1_T-1", "BEL_Zaventem-4_1_T-1")
+
+
+def unit_scenarios(src='/root/reference/scenarios', dst=os.path.join(ROOT, 'tests', 'golden', 'unit_scenarios.pkl.gz')):
+    out = {}
+    for name in UNIT_SCENARIOS:
+        out[name] = CommonRoadFileReader(os.path.join(src, name + '.xml')).open(lanelet_assignment=True)
+    with gzip.GzipFile(dst, 'wb', mtime=0) as f:
+        f.write(pickle.dumps(out, protocol=4))
+    print('wrote', dst, os.path.getsize(dst) / 1e3, 'kB')
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) < 2 or sys.argv[1] != 'unit':
+        main()
+    unit_scenarios()
