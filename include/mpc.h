@@ -42,6 +42,7 @@ extern "C" {
 #define MPC_MODE_NO_CULL 2u       /* skip the bounding-circle axis: every pair runs the full separating-axis test */
 #define MPC_MODE_NO_EARLY_EXIT 4u /* keep evaluating a tile after its primitives are all known to collide */
 #define MPC_MODE_COUNT_WORK 8u    /* instrumented launch: fill mpc_stats.axis_tests / cull_tests (slower) */
+#define MPC_MODE_NO_TIMING 16u    /* no CUDA events around the kernels: mpc_stats.ms_device stays 0 (saves a few us per call) */
 
 #define MPC_MAX_LIB_VERTS 16      /* vertices per primitive occupancy polygon (reference: 4, AROC export: <= 12) */
 #define MPC_MAX_OBST_VERTS 8      /* vertices per convex obstacle piece (reference scenarios: rectangles, triangles) */

@@ -12,6 +12,7 @@ MODE_VALIDATOR = 1
 MODE_NO_CULL = 2
 MODE_NO_EARLY_EXIT = 4
 MODE_COUNT_WORK = 8
+MODE_NO_TIMING = 16
 
 MAX_LIB_VERTS = 16
 MAX_OBST_VERTS = 8

@@ -9,8 +9,11 @@ Reference call sites served:
   collision_check(node, primitive, space, goal_set, param)        src/maneuverAutomatonPlannerStandalone.py:196-226
   collisionChecker(scenario, traj, param)                         auxiliary/collisionChecker.py:6-35
 """
+import ctypes as C
+
 import numpy as np
 
+from ._cabi import MODE_NO_TIMING
 from .engine import MODE_PLANNER, MODE_VALIDATOR, CollisionEngine, make_queries
 from .geometry import ring_segments, rings_of
 
@@ -225,6 +228,7 @@ class PrimitiveChecker:
                 pass
         self.index_of = {id(p): i for i, p in enumerate(MA.primitives)}
         self._set_len = np.diff(lay['set_off'])
+        self._set_len_list = [int(v) for v in self._set_len]
         self._qbuf = {}
         self.nscenes = 0
         self.mode = MODE_PLANNER
@@ -245,19 +249,21 @@ class PrimitiveChecker:
     def bucket_collides(self, x, y, phi, t0, step_limit, bucket, scenes=(0,)):
         """collision bits (True = collides) of every primitive of velocity bucket `bucket` appended at pose
         (x, y, phi) and time index t0; with several scenes a candidate collides if it does in any of them"""
-        cnt = int(self._set_len[bucket])
+        cnt = self._set_len_list[bucket]
         ns = len(scenes)
-        q = self._qbuf.get(ns)
-        if q is None:
-            q = self._qbuf[ns] = make_queries(ns)
-            q['cand_off'] = 0
-        q['x'], q['y'], q['c'], q['s'] = x, y, np.cos(phi), np.sin(phi)
-        q['t0'], q['step_limit'], q['cand_set'], q['cand_cnt'] = t0, step_limit, bucket, cnt
-        q['scene'] = scenes
+        ent = self._qbuf.get(ns)
+        if ent is None:
+            q = make_queries(ns)
+            ent = self._qbuf[ns] = (q, q.ctypes.data_as(C.c_void_p))     # data_as costs microseconds: once per buffer
+        q, qptr = ent
+        # one record assignment per scene (field-wise assignment costs 7 us); np.cos / np.sin like the reference
+        # (src/lowLevelPlannerManeuverAutomaton.py:121) so that the pose is the one the reference transforms with
+        c, sn = np.cos(phi), np.sin(phi)
+        for k in range(ns):
+            q[k] = (x, y, c, sn, scenes[k], t0, step_limit, bucket, 0, cnt, 0, 0)
         if hasattr(self.backend, 'query_fast'):
-            mask, st = self.backend.query_fast(q, self.mode, want_stats=True)
             nw = (cnt + 31) // 32
-            bits = np.unpackbits(mask.view(np.uint8).reshape(ns, nw * 4), axis=1, bitorder='little')[:, :cnt]
+            mask, st = self.backend.query_fast(q, self.mode | MODE_NO_TIMING, want_stats=True, nw=ns * nw, qptr=qptr)
             s = self.stats
             s['queries'] += 1
             s['candidates'] += cnt * ns
@@ -265,7 +271,10 @@ class PrimitiveChecker:
             s['near_tangent'] += st.near_tangent
             s['exact_ties'] += st.exact_ties
             s['pairs_nominal'] += st.pairs_nominal
-            return bits.any(axis=0) if ns > 1 else bits[0].astype(bool)
+            if ns == 1:
+                return np.unpackbits(mask.view(np.uint8), count=cnt, bitorder='little').view(np.bool_)
+            bits = np.unpackbits(mask.view(np.uint8).reshape(ns, nw * 4), axis=1, bitorder='little')[:, :cnt]
+            return bits.any(axis=0)
         bits, st = self.backend.query(q, None, self.mode)
         self._account(st, cnt * ns)
         return bits.reshape(ns, cnt).any(axis=0)
@@ -289,13 +298,14 @@ class PrimitiveChecker:
         (-1: goal not reached): (bits, cost, goal_step)"""
         cnt = int(self._set_len[bucket])
         ns = len(scenes)
-        q = self._qbuf.get(ns)
-        if q is None:
-            q = self._qbuf[ns] = make_queries(ns)
-            q['cand_off'] = 0
-        q['x'], q['y'], q['c'], q['s'] = x, y, np.cos(phi), np.sin(phi)
-        q['t0'], q['step_limit'], q['cand_set'], q['cand_cnt'] = t0, step_limit, bucket, cnt
-        q['scene'] = scenes
+        ent = self._qbuf.get(ns)
+        if ent is None:
+            q = make_queries(ns)
+            ent = self._qbuf[ns] = (q, q.ctypes.data_as(C.c_void_p))
+        q = ent[0]
+        c, sn = np.cos(phi), np.sin(phi)
+        for k in range(ns):
+            q[k] = (x, y, c, sn, scenes[k], t0, step_limit, bucket, 0, cnt, 0, 0)
         parent = self._pbuf.get(ns)
         if parent is None:
             parent = self._pbuf[ns] = np.zeros((ns, 2))

@@ -1101,11 +1101,12 @@ static int run_batch(mpc_ctx *ctx, uint32_t *out_mask, int mask_words, mpc_stats
     if (mask_words > 0 && !out_mask) return fail(ctx, MPC_E_ARG, "out_mask missing");
     float ms = 0.f;
     int kernels = 2, overflow = 0, rc;
-    rc = run_graph(ctx, &ms, stats != nullptr);
+    const bool timed = stats != nullptr && !(ctx->mode & MPC_MODE_NO_TIMING);
+    rc = run_graph(ctx, &ms, timed);
     if (!rc && ((const Counters *)ctx->h_res)->wl_count > (unsigned)ctx->wl_cap) {
         // refinement list overflowed: the plain path grows it and re-runs (and drops the graphs)
         rc = issue_uploads(ctx);
-        if (!rc) rc = run_once(ctx, &ms, &kernels, &overflow, stats != nullptr);
+        if (!rc) rc = run_once(ctx, &ms, &kernels, &overflow, timed);
         overflow = 1;
     }
     if (rc) return rc;

@@ -150,16 +150,20 @@ class CollisionEngine:
                                       int(mode), _cabi.ptr(mask), nw, C.byref(st)), "mpc_query")
         return mask[:nw], st.as_dict()
 
-    def query_fast(self, queries, mode=MODE_PLANNER, want_stats=False):
+    def query_fast(self, queries, mode=MODE_PLANNER, want_stats=False, nw=None, qptr=None):
         """low-overhead path for the planner loop: `queries` is a ready QUERY_DTYPE array that references staged
-        candidate sets only; returns the packed mask (a view into a reused buffer) and, optionally, the stats struct"""
-        nw = mask_words(queries)
+        candidate sets only; returns the packed mask (a view into a reused buffer) and, optionally, the stats struct.
+        `nw` (number of mask words of the batch) and `qptr` (ctypes pointer to `queries`) may be handed in by a caller
+        that knows them: computing them costs 6 + 4 us of the ~50 us a planner-sized query takes"""
+        if nw is None:
+            nw = mask_words(queries)
         buf = getattr(self, '_mask_buf', None)
         if buf is None or len(buf) < nw:
             buf = self._mask_buf = np.zeros(max(nw, 64), dtype=np.uint32)
             self._mask_ptr = buf.ctypes.data_as(C.c_void_p)
         st = self._stats_buf = getattr(self, '_stats_buf', None) or _cabi.Stats()
-        rc = self._L.mpc_query(self._ctx, len(queries), queries.ctypes.data_as(C.c_void_p), None, 0, int(mode),
+        rc = self._L.mpc_query(self._ctx, len(queries), qptr if qptr is not None else queries.ctypes.data_as(C.c_void_p),
+                               None, 0, int(mode),
                                self._mask_ptr, nw, C.byref(st) if want_stats else None)
         if rc != 0:
             self._check(rc, "mpc_query")

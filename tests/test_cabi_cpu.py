@@ -38,7 +38,8 @@ def test_struct_layouts_match_header():
 def test_mode_constants_match_header():
     src = open(os.path.join(ROOT, "include", "mpc.h")).read()
     for name, val in (("MPC_MODE_VALIDATOR", _cabi.MODE_VALIDATOR), ("MPC_MODE_NO_CULL", _cabi.MODE_NO_CULL),
-                      ("MPC_MODE_NO_EARLY_EXIT", _cabi.MODE_NO_EARLY_EXIT), ("MPC_MODE_COUNT_WORK", _cabi.MODE_COUNT_WORK)):
+                      ("MPC_MODE_NO_EARLY_EXIT", _cabi.MODE_NO_EARLY_EXIT), ("MPC_MODE_COUNT_WORK", _cabi.MODE_COUNT_WORK),
+                      ("MPC_MODE_NO_TIMING", _cabi.MODE_NO_TIMING)):
         m = re.search(r"#define\s+%s\s+(\d+)u" % name, src)
         assert m and int(m.group(1)) == val
     assert int(re.search(r"#define\s+MPC_MAX_LIB_VERTS\s+(\d+)", src).group(1)) == _cabi.MAX_LIB_VERTS

@@ -260,8 +260,8 @@ def test_reference_unit_test_scenarios_on_gpu(MA, name, max_nodes, expect_plan):
     from motionplanner_b200.engine import CollisionEngine
 
     class Logged(CollisionEngine):
-        def query_fast(self, queries, mode=0, want_stats=False):
-            mask, st = super().query_fast(queries, mode, want_stats)
+        def query_fast(self, queries, mode=0, want_stats=False, **kw):
+            mask, st = super().query_fast(queries, mode, want_stats, **kw)
             self.bits.append(mask.copy())
             return mask, st
 
