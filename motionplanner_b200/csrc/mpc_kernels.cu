@@ -84,6 +84,8 @@ struct mpc_ctx {
     long long meta_sig = 0;
     // queries
     DevBuf qpack_d, cand_d, res_d, wl, flush;
+    void *res_p = nullptr;        // result block of the prepared batch: inside qpack_d (fused_clear) or res_d
+    bool fused_clear = false;     // small result blocks are cleared by the zeros the query upload carries
     size_t qpack_cta_off = 0, qpack_hdr_off = 0, up_bytes = 0, up_cand_bytes = 0, up_cand_src = 0;
     unsigned long long generation = 0;          // bumped whenever a pointer a captured graph holds may have changed
     std::map<std::vector<long long>, cudaGraphExec_t> graphs;
@@ -781,7 +783,7 @@ static KParams make_params(mpc_ctx *ctx) {
     p.cand_pos = (const int *)ctx->sets_pos.p;
     p.cand_inv = p.cand_pos + ctx->set_total;
     p.B = ctx->B;
-    p.cnt = (Counters *)ctx->res_d.p; p.mask = (unsigned *)((char *)ctx->res_d.p + sizeof(Counters));
+    p.cnt = (Counters *)ctx->res_p; p.mask = (unsigned *)((char *)ctx->res_p + sizeof(Counters));
     p.mask_sorted = p.mask + ctx->mask_words;
     p.nwords = ctx->mask_words;
     p.wl = (int4 *)ctx->wl.p; p.wl_cap = ctx->wl_cap;
@@ -846,11 +848,11 @@ static cudaError_t raise_smem_limits(const cudaDeviceProp &prop) {
     return raise_smem_va_vb<16, 8>(bytes);
 }
 
-static int launch_all(mpc_ctx *ctx, cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2) {
+static int launch_all(mpc_ctx *ctx, cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2, bool clear = true) {
     KParams p = make_params(ctx);
     cudaStream_t st = ctx->stream;
     if (e0) CU(cudaEventRecord(e0, st));
-    CU(cudaMemsetAsync(ctx->res_d.p, 0, sizeof(Counters) + (size_t)2 * ctx->mask_words * sizeof(unsigned), st));
+    if (clear) CU(cudaMemsetAsync(ctx->res_p, 0, sizeof(Counters) + (size_t)2 * ctx->mask_words * sizeof(unsigned), st));
     if (e1) CU(cudaEventRecord(e1, st));
     CU(launch_check(ctx, p));
     if (e2) CU(cudaEventRecord(e2, st));
@@ -870,7 +872,7 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
     CU(cudaSetDevice(ctx->device));
     ctx->prepared = false;
     // grid shape: groups of 32 candidates, gpc groups per CTA; aim for a few CTAs per SM
-    long long total_groups = 0;
+    long long total_groups = 0, total_words = 0;
     for (int q = 0; q < B; q++) {
         const mpc_query_desc &d = queries[q];
         if (d.scene < 0 || d.scene >= ctx->nscenes) return fail(ctx, MPC_E_ARG, "query %d: scene %d outside 0..%d", q, d.scene, ctx->nscenes - 1);
@@ -883,6 +885,7 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
             if (d.cand_off + d.cand_cnt > ncand || (d.cand_cnt > 0 && !cand_idx)) return fail(ctx, MPC_E_ARG, "query %d: range exceeds cand_idx (%d)", q, ncand);
         }
         total_groups += ((long long)d.cand_cnt + 31) / 32 * ctx->J;
+        total_words += ((long long)d.cand_cnt + 31) / 32;
     }
     for (int i = 0; i < ncand; i++)
         if (cand_idx[i] < 0 || cand_idx[i] >= ctx->P) return fail(ctx, MPC_E_ARG, "cand_idx[%d]=%d outside the library", i, cand_idx[i]);
@@ -922,11 +925,19 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
     // pack: QDev[B], cta_off[B+1] (one copy), explicit candidates (second copy, only when present)
     size_t bytes_q = sizeof(QDev) * (size_t)std::max(B, 1), bytes_c = (sizeof(int) * (size_t)(B + 1) + 15) / 16 * 16;
     const size_t bytes_h = 16, bytes_i = sizeof(int) * (size_t)ncand;
-    CU(ensure_pinned(ctx, bytes_q + bytes_c + bytes_h + bytes_i + 64));
+    // a small result block (counters + two mask arrays) sits behind the query pack in the same device buffer and is
+    // cleared by zeros appended to the upload: one copy node instead of copy + memset in the replayed graph
+    const size_t up0 = bytes_q + bytes_c + bytes_h;
+    const size_t clear_bytes = sizeof(Counters) + sizeof(unsigned) * (size_t)2 * (size_t)total_words;
+    const bool fused = clear_bytes <= 8192;
+    const size_t zoff = (up0 + 255) & ~(size_t)255, zbytes = fused ? (clear_bytes + 15) / 16 * 16 : 0;
+    const size_t cand_src = fused ? zoff + zbytes : up0;
+    CU(ensure_pinned(ctx, cand_src + bytes_i + 64));
+    if (fused) memset((char *)ctx->h_pin + up0, 0, zoff + zbytes - up0);
     QDev *hq = (QDev *)ctx->h_pin;
     int *hcta = (int *)((char *)ctx->h_pin + bytes_q);
     float *hhdr = (float *)((char *)ctx->h_pin + bytes_q + bytes_c);
-    int *hidx = (int *)((char *)ctx->h_pin + bytes_q + bytes_c + bytes_h);
+    int *hidx = (int *)((char *)ctx->h_pin + cand_src);
     long long ctas = 0, words = 0;
     double maxq = 0.0;
     for (int q = 0; q < B; q++) {
@@ -965,12 +976,14 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
     ctx->maxabs_query = std::nextafter((float)maxq, INFINITY);
     hhdr[0] = ctx->maxabs_query;
     hhdr[1] = hhdr[2] = hhdr[3] = 0.f;
-    CU(ensure(ctx, ctx->qpack_d, bytes_q + bytes_c + bytes_h));
+    if (words != total_words) return fail(ctx, MPC_E_STATE, "internal: mask word count");
+    CU(ensure(ctx, ctx->qpack_d, fused ? zoff + zbytes : up0));
     ctx->qpack_cta_off = bytes_q;
     ctx->qpack_hdr_off = bytes_q + bytes_c;
-    ctx->up_bytes = bytes_q + bytes_c + bytes_h;
+    ctx->up_bytes = fused ? zoff + zbytes : up0;
     ctx->up_cand_bytes = bytes_i;
-    ctx->up_cand_src = bytes_q + bytes_c + bytes_h;
+    ctx->up_cand_src = cand_src;
+    ctx->fused_clear = fused;
     // candidate arena = staged sets followed by this call's explicit lists
     size_t arena = sizeof(int) * (size_t)std::max(2 * ctx->set_total + ncand, 1);
     void *arena_before = ctx->cand_d.p;
@@ -980,6 +993,7 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
     ctx->arena_valid = true;
     CU(ensure(ctx, ctx->res_d, sizeof(Counters) + sizeof(unsigned) * (size_t)2 * std::max<long long>(words, 1)));
     CU(ensure_result_host(ctx, sizeof(Counters) + sizeof(unsigned) * (size_t)std::max<long long>(words, 1)));
+    ctx->res_p = fused ? (void *)((char *)ctx->qpack_d.p + zoff) : ctx->res_d.p;
     ctx->B = B; ctx->ctas = (int)ctas; ctx->mask_words = (int)words; ctx->mode = mode;
     ctx->prepared = true;
     if (upload) return issue_uploads(ctx);
@@ -1043,7 +1057,7 @@ static int run_once(mpc_ctx *ctx, float *ms, int *kernels, int *overflow, bool t
         if (rc) return rc;
         *kernels += 2;
         if (timed) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-        CU(cudaMemcpyAsync(ctx->h_res, ctx->res_d.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->h_res, ctx->res_p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         if (timed) CU(cudaEventElapsedTime(ms, ctx->ev[0], ctx->ev[1]));
         const Counters *c = (const Counters *)ctx->h_res;
@@ -1060,7 +1074,7 @@ static int run_once(mpc_ctx *ctx, float *ms, int *kernels, int *overflow, bool t
 // by one.  Graphs are keyed by everything that is baked into their nodes and dropped whenever a buffer moves.
 static int run_graph(mpc_ctx *ctx, float *ms, bool timed) {
     const size_t bytes = sizeof(Counters) + (size_t)ctx->mask_words * sizeof(unsigned);
-    std::vector<long long> key = {(long long)ctx->B, (long long)ctx->ctas, (long long)ctx->mask_words, (long long)ctx->mode,
+    std::vector<long long> key = {(long long)ctx->B, (long long)ctx->ctas, (long long)ctx->fused_clear, (long long)ctx->mask_words, (long long)ctx->mode,
                                   (long long)ctx->gpc, (long long)ctx->cap_o, (long long)ctx->cap_s, (long long)ctx->smem,
                                   (long long)ctx->up_bytes, (long long)ctx->up_cand_bytes, (long long)ctx->wl_cap,
                                   (long long)ctx->VA, (long long)ctx->VB, (long long)ctx->ob_stride, (long long)ctx->sg_stride,
@@ -1072,9 +1086,9 @@ static int run_graph(mpc_ctx *ctx, float *ms, bool timed) {
         cudaGraph_t graph = nullptr;
         CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
         int rc = issue_uploads(ctx);
-        if (!rc) rc = launch_all(ctx, nullptr, nullptr, nullptr);
+        if (!rc) rc = launch_all(ctx, nullptr, nullptr, nullptr, !ctx->fused_clear);     // the upload just cleared it
         cudaError_t e1 = cudaSuccess;
-        if (!rc) e1 = cudaMemcpyAsync(ctx->h_res, ctx->res_d.p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        if (!rc) e1 = cudaMemcpyAsync(ctx->h_res, ctx->res_p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
         cudaError_t e2 = cudaStreamEndCapture(ctx->stream, &graph);
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (e1 != cudaSuccess || e2 != cudaSuccess) {
@@ -1159,7 +1173,7 @@ extern "C" int mpc_run_prepared(mpc_ctx *ctx, int iters, int flush_l2, float *ms
         kernels += 2;
     }
     const size_t bytes = sizeof(Counters) + (size_t)ctx->mask_words * sizeof(unsigned);
-    CU(cudaMemcpyAsync(ctx->h_res, ctx->res_d.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_res, ctx->res_p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     fill_stats(ctx, stats, ms, kernels, overflow);
     return MPC_OK;
@@ -1170,7 +1184,7 @@ extern "C" int mpc_fetch_mask(mpc_ctx *ctx, uint32_t *out_mask, int mask_words) 
     if (!ctx->prepared) return fail(ctx, MPC_E_STATE, "no prepared batch");
     if (mask_words != ctx->mask_words) return fail(ctx, MPC_E_ARG, "mask_words=%d but the batch needs %d", mask_words, ctx->mask_words);
     if (mask_words) {
-        CU(cudaMemcpyAsync(out_mask, (const char *)ctx->res_d.p + sizeof(Counters), sizeof(unsigned) * (size_t)mask_words, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(out_mask, (const char *)ctx->res_p + sizeof(Counters), sizeof(unsigned) * (size_t)mask_words, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }
     return MPC_OK;
