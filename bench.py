@@ -179,7 +179,7 @@ def main():
     ap.add_argument("--queries", type=int, default=64,
                     help="queries (ego poses) per step; default = the 64 jittered poses SURVEY.md 8(d) defines for C4")
     ap.add_argument("--ref-queries", type=int, default=2, help="queries per step of the CPU reference arm (bounded sample)")
-    ap.add_argument("--lanes", type=int, default=3,
+    ap.add_argument("--lanes", type=int, default=4,
                     help="contexts per GPU for the end-to-end figure (1 = one context, strictly serial steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

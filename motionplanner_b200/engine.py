@@ -118,6 +118,14 @@ class CollisionEngine:
 
     # -- scenes --------------------------------------------------------------------------------------------------
     def set_scenes(self, scene_step_off, origins, step_obst_off, obst, obst_nv, step_seg_begin, step_seg_end, segs):
+        self.set_scenes_args(self.scene_args(scene_step_off, origins, step_obst_off, obst, obst_nv, step_seg_begin,
+                                             step_seg_end, segs))
+
+    @staticmethod
+    def scene_args(scene_step_off, origins, step_obst_off, obst, obst_nv, step_seg_begin, step_seg_end, segs):
+        """checks the arrays and marshals them into the argument tuple of mpc_set_scenes (the arrays are kept alive by
+        the tuple).  A cycle that refills the same (page-locked) arrays every time marshals once and calls
+        set_scenes_args per cycle: the conversions and pointer look-ups cost ~40 us of interpreter time per call."""
         scene_step_off = _arr(scene_step_off, np.int32)
         nscenes = len(scene_step_off) - 1
         origins = _arr(origins, np.float64).reshape(nscenes, 2)
@@ -133,10 +141,15 @@ class CollisionEngine:
         step_seg_end = _arr(step_seg_end, np.int32)
         assert len(step_seg_begin) == len(step_seg_end) == nsteps
         segs = _arr(segs if segs is not None else np.zeros((0, 4)), np.float64).reshape(-1, 4)
-        self._check(self._L.mpc_set_scenes(self._ctx, nscenes, _cabi.ptr(scene_step_off), _cabi.ptr(origins),
-                                           _cabi.ptr(step_obst_off), _cabi.ptr(obst), _cabi.ptr(obst_nv),
-                                           int(obst.shape[1]), _cabi.ptr(step_seg_begin), _cabi.ptr(step_seg_end),
-                                           _cabi.ptr(segs), len(segs)), "mpc_set_scenes")
+        keep = (scene_step_off, origins, step_obst_off, obst, obst_nv, step_seg_begin, step_seg_end, segs)
+        return (nscenes, _cabi.ptr(scene_step_off), _cabi.ptr(origins), _cabi.ptr(step_obst_off), _cabi.ptr(obst),
+                _cabi.ptr(obst_nv), int(obst.shape[1]), _cabi.ptr(step_seg_begin), _cabi.ptr(step_seg_end),
+                _cabi.ptr(segs), len(segs), keep)
+
+    def set_scenes_args(self, args):
+        rc = self._L.mpc_set_scenes(self._ctx, *args[:11])
+        if rc != 0:
+            self._check(rc, "mpc_set_scenes")
 
     # -- queries -------------------------------------------------------------------------------------------------
     def query_mask(self, queries, cand_idx=None, mode=MODE_PLANNER):

@@ -13,9 +13,12 @@ Every decision is still made by the kernels of csrc/mpc_device.cuh; results do n
 Reference being replaced: the per-scenario loop of evaluation/runAllScenarios.py:56-99 around `collision_check`
 (src/lowLevelPlannerManeuverAutomaton.py:95-125).
 """
+import ctypes as C
 import threading
 
-from .engine import MODE_PLANNER, CollisionEngine
+import numpy as np
+
+from .engine import MODE_PLANNER, QUERY_DTYPE, CollisionEngine, mask_words
 
 __all__ = ["CollisionLanes"]
 
@@ -51,6 +54,16 @@ class CollisionLanes:
         out = [None] * len(cycles)
         errors = []
         stop = threading.Event()
+        # marshal every distinct scene / query array once (a producer that refills the same page-locked arrays hands
+        # the same objects in again): the per-cycle interpreter time under the GIL is what the lanes compete for
+        scene_args, query_args = {}, {}
+        cand = None if cand_idx is None else np.ascontiguousarray(cand_idx, dtype=np.int32)
+        for scene, queries in cycles:
+            if scene is not None and id(scene) not in scene_args:
+                scene_args[id(scene)] = CollisionEngine.scene_args(*[scene[k] for k in SCENE_KEYS])
+            if id(queries) not in query_args:
+                q = np.ascontiguousarray(queries, dtype=QUERY_DTYPE)
+                query_args[id(queries)] = (q, q.ctypes.data_as(C.c_void_p), mask_words(q))
 
         def work(lane):
             eng = self.engines[lane]
@@ -60,9 +73,13 @@ class CollisionLanes:
                         return
                     scene, queries = cycles[i]
                     if scene is not None:
-                        eng.set_scenes(*[scene[k] for k in SCENE_KEYS])
-                    mask, st = eng.query_mask(queries, cand_idx, mode)
-                    out[i] = (mask, st)
+                        eng.set_scenes_args(scene_args[id(scene)])
+                    q, qptr, nw = query_args[id(queries)]
+                    if cand is None:
+                        mask, st = eng.query_fast(q, mode, want_stats=True, nw=nw, qptr=qptr)
+                        out[i] = (mask[:nw].copy(), {k: getattr(st, k) for k, _ in st._fields_})
+                    else:
+                        out[i] = eng.query_mask(q, cand, mode)
             except BaseException as exc:          # noqa: BLE001 -- handed to the caller below
                 errors.append(exc)
                 stop.set()
