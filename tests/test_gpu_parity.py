@@ -543,3 +543,38 @@ def test_lanes_match_single_context(eng):
         assert all(np.array_equal(a[0], b[0]) for a, b in zip(res, res2))
     finally:
         lanes.close()
+
+
+def test_scout_launch_regime(eng, monkeypatch):
+    """batches whose time slots fill only a fraction of the resident wave launch the first slot of the order on its own
+    (finer CTAs), the rest with its bits visible: bits and the nominal pair count equal the oracle's; forcing 0 / 2 / 3
+    scout launches and other scout CTA sizes on the same batch changes nothing"""
+    lib, sc, org, q = W.c4_problem(P=4096, O_lanes=8, slots=16, T=12, nqueries=32)
+    rng = np.random.default_rng(5)
+    q["t0"][5], q["step_limit"][7], q["cand_cnt"][9], q["cand_cnt"][11] = 2, 6, 1000, 0
+    q["cand_off"][13], q["cand_cnt"][13] = 77, 3001
+    stage(eng, lib, sc, org)
+    pb = orc.Problem(lib, sc)
+    want, ost = pb.check(q, None, orc.MODE_NO_EARLY_EXIT)
+    got, st = eng.query(q, None, MODE_PLANNER)
+    assert st["kernels"] == 3                                  # scout + main + refine: the heuristic picked the regime
+    assert np.array_equal(got, want) and st["pairs_nominal"] == ost["pairs_nominal"]
+    wantv, _ = pb.check(q, None, orc.MODE_STRICT | orc.MODE_NO_EARLY_EXIT)
+    gotv, _ = eng.query(q, None, MODE_VALIDATOR)
+    assert np.array_equal(gotv, wantv)
+    for scouts, sgpc in ((0, None), (2, None), (3, 8), (1, 40), (1, 128)):
+        monkeypatch.setenv("MPC_SCOUTS", str(scouts))
+        if sgpc is None:
+            monkeypatch.delenv("MPC_SCOUT_GPC", raising=False)
+        else:
+            monkeypatch.setenv("MPC_SCOUT_GPC", str(sgpc))
+        got2, st2 = eng.query(q, None, MODE_PLANNER)
+        assert st2["kernels"] == 2 + scouts
+        assert np.array_equal(got2, want) and st2["pairs_nominal"] == ost["pairs_nominal"], (scouts, sgpc)
+    # small problems with forced scouts (multi-phase tiles, general polygons, explicit lists)
+    monkeypatch.setenv("MPC_SCOUTS", "2")
+    monkeypatch.delenv("MPC_SCOUT_GPC", raising=False)
+    for seed, kw in ((31, dict()), (32, dict(lib_verts=9, obst_verts=7)), (33, dict(max_obst=400, P=40, J=9, nsteps=10))):
+        lib2, sc2, org2, q2 = W.adversarial_problem(seed, **kw)
+        got3, want3, st3, ost3 = both(eng, lib2, sc2, org2, q2, None, MODE_PLANNER)
+        assert np.array_equal(got3, want3) and st3["pairs_nominal"] == ost3["pairs_nominal"]
