@@ -41,8 +41,8 @@ FLOP_PER_CHECK = 304            # rectangle x rectangle SAT, a =
 SAT_FLOP_EXECUTED = 160         # this kernel's full 4x4 test: 64 FMA (2 flop) + 24 min + 8 max
 CULL_FLOP_EXECUTED = 6          # centre-line axis per pair: 2 add + 2 fma (packed FADD2/FFMA2: two pairs per instruction)
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # no FP32 entry in MEASURED_PEAKS.json: derived from its sm_max_mhz
-NCU_DRAM_BYTES_PER_LAUNCH = 6521600    # ncu capture l (profiles/): dram__bytes_read.sum of one 64-query launch; write 2 KB
-NCU_WARP_INST_PER_LAUNCH = 90259337   # same capture: smsp__inst_executed.sum of that launch (a count, not a time)
+NCU_DRAM_BYTES_PER_LAUNCH = 4896512    # ncu capture n (profiles/): dram__bytes_read.sum of the two k_check launches (scout 0.46 MB + main 4.44 MB) of one 64-query step; write 0
+NCU_WARP_INST_PER_LAUNCH = 54931122   # same capture: smsp__inst_executed.sum of both launches (scout 10.99 M + main 43.94 M; a count, not a time)
 ISSUE_PEAK = 148 * 4 * 1.965e9         # warp instructions per second: 4 schedulers per SM, one issue per clock
 METRIC = "primitive x obstacle x timestep collision checks/sec"
 WORKLOAD = ("C4 dense traffic: 4096 primitives x 256 obstacles x 50 timesteps per query (BASELINE.json configs[3])")
@@ -349,11 +349,14 @@ def main():
                     "what": "CollisionEngine.set_scenes + query_mask (mpc_set_scenes + mpc_query) from pinned host "
                             "numpy buffers, every step" + ("" if e2e_lanes == 1 else "; steps dealt round-robin to %d "
                             "contexts on the GPU, one host thread each (CollisionLanes.run_cycles), so one step's "
-                            "copies overlap another's k_check" % e2e_lanes),
+                            "copies, staging kernels and launch boundaries overlap another's k_check; no L2 flush "
+                            "between steps here, which is why it can exceed `value` (single stream, L2 flushed)"
+                            % e2e_lanes),
                     "single_context": {"value": world * args.steps * checks_step / e2e_serial_s,
                                        "ms_per_step": 1e3 * e2e_serial_s / args.steps}},
-            "gpu_launches": int(args.steps * 3),
-            "gpu_launches_what": "per timed step: k_fill_u32 (L2 flush, outside the event bracket), k_check, k_refine",
+            "gpu_launches": int(args.steps * (1 + st["kernels"] // (args.steps + 1))),
+            "gpu_launches_what": "per timed step: k_fill_u32 (L2 flush, outside the event bracket), k_check (scout launch "
+                                 "of the first time slot + the rest of the grid when the batch qualifies), k_refine",
             "clocks": clocks,
             "roofline": {
                 "bound": "fp32", "kernel": "k_check<4,4,0,0,0>", "achieved": exec_tflops, "peak": FP32_PEAK_TFLOPS,
@@ -361,13 +364,14 @@ def main():
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH if nq == 64 else None,
                 "what": "executed FP32 flop of the timed launch (an instrumented launch of the same batch counts "
                         "centre-line axis tests x 6 flop and full separating-axis tests x 160 flop) / CUDA-event "
-                        "duration of k_check. The kernel is NOT FP32-bound and is not meant to be: 80 % of the nominal "
-                        "pairs are never looked at (their candidate already collides at another time step -- the "
-                        "reference's early return), sub-block bounding boxes separate 17 %, the centre-line axis all "
-                        "but 0.06 % of the rest. ncu (profiles/r01l_k_check_ncu_full.csv): instruction issue 65 % of "
-                        "peak (see issue_slots), ALU pipe 43 %, FMA pipe 18 %; HBM traffic is below the algorithmic "
-                        "bytes because skipped tiles are never fetched. The arithmetic rate of the full test is "
-                        "full_evaluation (no culling, no exits): 57 % of the FP32 peak.",
+                        "duration of k_check (scout launch + main launch). The kernel is NOT FP32-bound and is not meant to "
+                        "be: 93 % of the nominal pairs are never looked at (their candidate already collides at another "
+                        "time step -- the reference's early return), sub-block bounding boxes separate most of the "
+                        "rest, the centre-line axis all but 0.04 %. ncu (profiles/r01n_k_check_ncu_full.csv, both "
+                        "launches): instruction issue 54-57 % of the active cycles (see issue_slots), ALU pipe 33-36 %, "
+                        "FMA pipe 14-15 %; HBM traffic is below the algorithmic bytes because skipped tiles are never "
+                        "fetched. The arithmetic rate of the full test is full_evaluation (no culling, no exits): "
+                        "55-57 % of the FP32 peak.",
                 "peak_source": "derived: 148 SM x 128 lanes x 2 x sm_max_mhz 1965 (MEASURED_PEAKS.json has no FP32 "
                                "figure)",
                 "kernel_ms": main_ms,
@@ -396,10 +400,12 @@ def main():
                                 "note": "the binding resource per ncu: executed warp instructions of one launch (count "
                                         "from the committed capture) / live CUDA-event duration, against 148 SM x 4 "
                                         "schedulers x sm_max_mhz"},
-                "ncu": {"source": "profiles/r01l_k_check_ncu_full.csv", "smsp__issue_active_pct": 58.2,
-                        "l1tex__data_pipe_lsu_wavefronts_pct": 32.1, "sm__inst_executed_pipe_fma_pct": 15.2,
-                        "sm__inst_executed_pipe_alu_pct": 36.5, "smsp__inst_executed": NCU_WARP_INST_PER_LAUNCH,
-                        "dram__bytes_read": NCU_DRAM_BYTES_PER_LAUNCH, "dram__bytes_write": 2048,
+                "ncu": {"source": "profiles/r01n_k_check_ncu_full.csv", "launches": "scout (512 CTAs, 24.3 us under ncu) "
+                        "+ main (3136 CTAs, 79.4 us)", "smsp__issue_active_pct": [56.8, 53.8],
+                        "l1tex__data_pipe_lsu_wavefronts_pct": [22.4, 30.5], "sm__inst_executed_pipe_fma_pct": [15.2, 13.8],
+                        "sm__inst_executed_pipe_alu_pct": [35.5, 33.2], "sm__warps_active_pct": [38.0, 33.9],
+                        "smsp__inst_executed": NCU_WARP_INST_PER_LAUNCH,
+                        "dram__bytes_read": NCU_DRAM_BYTES_PER_LAUNCH, "dram__bytes_write": 0,
                         "note": "which tiles are skipped depends on scheduling: counts vary by a few percent between launches"},
                 "hbm": {"algorithmic_bytes": algo_bytes, "achieved_gbs": algo_bytes / (main_ms * 1e-3) / 1e9,
                         "peak_gbs": hbm_peak, "frac": algo_bytes / (main_ms * 1e-3) / 1e9 / hbm_peak,

@@ -964,10 +964,19 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
         }
         return c;
     };
-    int scouts = 0;
+    int scouts = 0, sg = nwarps;               // sg: groups per CTA of the scout launch, one slot ~ one resident wave
     {
+        long long groups_slot = 0;
+        for (int q = 0; q < B; q++) groups_slot += (queries[q].cand_cnt + 31) / 32;
+        sg = (int)((groups_slot + resident - 1) / std::max<long long>(resident, 1));
+        sg = std::max(nwarps, std::min((sg + nwarps - 1) / nwarps * nwarps, gpc));
+        if (const char *e = getenv("MPC_SCOUT_GPC")) sg = std::max(1, std::min(atoi(e), GPC_MAX));             // tuning hook
         const long long c = ctas_per_slot(gpc);
-        if (!(mode & (MPC_MODE_NO_EARLY_EXIT | MPC_MODE_NO_CULL)) && ctx->J >= 8 && c > 0 && 2 * c <= resident && c * ctx->J >= 2 * resident)
+        // worth it when a slot fills less than half the wave, the grid is at least two waves, and the scout itself puts
+        // a CTA on most SMs (C4, ms per batch of 4 / 8 / 16 / 32 / 64 queries: 0.045 / 0.073 / 0.082 / 0.097 / 0.129
+        // without, 0.052 / 0.046 / 0.064 / 0.077 / 0.104 with)
+        if (!(mode & (MPC_MODE_NO_EARLY_EXIT | MPC_MODE_NO_CULL)) && ctx->J >= 8 && c > 0 && 2 * c <= resident && c * ctx->J >= 2 * resident &&
+            ctas_per_slot(sg) * 8 >= resident)
             scouts = 1;
         if (const char *e = getenv("MPC_SCOUTS")) scouts = std::max(0, std::min(atoi(e), ctx->J - 1));      // tuning hook
         if (scouts && gpc == gpc_cap && gpc < GPC_MAX) {
@@ -1036,11 +1045,6 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
     hcta[B] = (int)ctas;
     // CTA table of the scout launch: groups per CTA such that one time slot fills the resident wave
     {
-        long long groups_slot = 0;
-        for (int q = 0; q < B; q++) groups_slot += (queries[q].cand_cnt + 31) / 32;
-        int sg = (int)((groups_slot + resident - 1) / std::max<long long>(resident, 1));
-        sg = std::max(nwarps, std::min((sg + nwarps - 1) / nwarps * nwarps, gpc));
-        if (const char *e = getenv("MPC_SCOUT_GPC")) sg = std::max(1, std::min(atoi(e), GPC_MAX));             // tuning hook
         int *hcta2 = hcta + bytes_c1 / sizeof(int);
         long long c2 = 0;
         for (int q = 0; q < B; q++) {
