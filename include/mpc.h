@@ -11,7 +11,9 @@
  *   - the caller owns all host buffers (plain pointers + sizes, little-endian, C order); the library owns all device
  *     memory.  Host buffers may be reused as soon as a call returns.
  *   - one context <=> one device + one CUDA stream.  A context is not thread-safe; contexts are independent (one per
- *     GPU, one process per GPU in the multi-GPU harness).  Calls do not hold the Python GIL (ctypes releases it).
+ *     GPU, one process per GPU in the multi-GPU harness) and share no mutable state, so several contexts on the SAME
+ *     device may be driven from different host threads at once: the copies and staging kernels of one overlap the
+ *     check kernels of another (motionplanner_b200/lanes.py).  Calls do not hold the Python GIL (ctypes releases it).
  *   - all geometry comes in as float64 in the caller's global frame, exactly the numbers the reference hands to
  *     shapely.  Re-centring to a scene-local frame and the float32 cast happen inside, on the device.
  *   - decisions are exact with respect to those float64 vertices: a float32 separating-axis pass with a conservative
