@@ -29,7 +29,13 @@ class CollisionLanes:
     def __init__(self, device=0, lanes=2):
         if lanes < 1:
             raise ValueError("lanes must be >= 1")
-        self.engines = [CollisionEngine(device) for _ in range(lanes)]
+        self.engines = []
+        try:
+            for _ in range(lanes):
+                self.engines.append(CollisionEngine(device))
+        except Exception:
+            self.close()
+            raise
 
     def __len__(self):
         return len(self.engines)
