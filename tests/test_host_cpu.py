@@ -163,3 +163,24 @@ def test_planner_queries_against_exact_oracle(MA):
                 ok = ok and not ex.convex_interiors_overlap(A, B)
             collide = collide or not ok
         assert bool(out[i]) == collide
+
+
+def test_scene_args_marshalling_without_a_device():
+    """CollisionEngine.scene_args checks and marshals the arrays of mpc_set_scenes once (lanes reuse the tuple every
+    cycle); it needs no context, keeps the converted arrays alive and rejects inconsistent shapes"""
+    from motionplanner_b200 import workloads as W
+    from motionplanner_b200.engine import CollisionEngine
+    lib, sc, org, q = W.adversarial_problem(3)
+    keys = ("scene_step_off", "origins", "step_obst_off", "obst", "obst_nv", "step_seg_begin", "step_seg_end", "segs")
+    scene = dict(sc, origins=org)
+    args = CollisionEngine.scene_args(*[scene[k] for k in keys])
+    assert len(args) == 12 and args[0] == 1 and args[6] == sc["obst"].shape[1] and args[10] == len(sc["segs"])
+    keep = args[11]
+    assert keep[3].dtype == np.float64 and keep[3].flags.c_contiguous and keep[4].dtype == np.int32
+    assert args[4].value == keep[3].ctypes.data                     # pointer to the kept obstacle array
+    bad = dict(scene, obst_nv=sc["obst_nv"][:-1])
+    with pytest.raises(AssertionError):
+        CollisionEngine.scene_args(*[bad[k] for k in keys])
+    none = dict(scene, obst=None, obst_nv=None, step_obst_off=np.zeros_like(sc["step_obst_off"]))
+    a2 = CollisionEngine.scene_args(*[none[k] for k in keys])
+    assert a2[4] is None and a2[5] is None                           # no obstacles: null pointers, as the ABI allows
