@@ -337,8 +337,10 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "queries_per_step": nq,
                        "queries_what": "one step = one batch of ego poses (seed 2 jitter) against one staged scene",
-                       "checks_per_step": checks_step, "seeds": [0, 1, 2], "l2": "flushed before every timed step "
-                       "(256 MiB fill)", "early_exit": "reference semantics (return at the first violation): warp-wide per tile, and whole "
+                       "checks_per_step": checks_step, "seeds": [0, 1, 2], "l2": "value: flushed before every timed step "
+                       "(256 MiB fill, outside the event bracket); e2e: wall clock over whole cycles, no flush (the "
+                       "library stays L2-resident between cycles as in a planner's steady state; warm_l2 gives the "
+                       "device time without the flush, ~5 % below the flushed one)", "early_exit": "reference semantics (return at the first violation): warp-wide per tile, and whole "
                        "groups / CTAs whose candidates already collide at another time step skip their tile; the "
                        "no-exit, no-cull rate is roofline.full_evaluation", "parallelism": "replicated library, "
                        "queries sharded per GPU, no collective on the hot path"},
