@@ -42,25 +42,35 @@ def close_engines():
 # ---------------------------------------------------------------------------------------------------------------------
 
 def _is_convex(v):
+    """all turns in one direction AND one revolution in total (a self-wrapping ring also turns one way throughout)"""
     d1 = np.roll(v, -1, axis=0) - v
     d2 = np.roll(v, -2, axis=0) - np.roll(v, -1, axis=0)
     c = d1[:, 0] * d2[:, 1] - d1[:, 1] * d2[:, 0]
-    return bool(np.all(c >= 0) or np.all(c <= 0))
+    if not (np.all(c >= 0) or np.all(c <= 0)):
+        return False
+    if not np.any(c):
+        return True           # all vertices collinear: a degenerate (zero-area) piece, dropped by the staging kernel
+    turn = np.arctan2(c, d1[:, 0] * d2[:, 0] + d1[:, 1] * d2[:, 1]).sum()
+    return bool(abs(abs(turn) - 2 * np.pi) < 1e-6)
+
+
+def _area2(v):
+    return float(np.sum(v[:, 0] * np.roll(v[:, 1], -1) - np.roll(v[:, 0], -1) * v[:, 1]))
 
 
 def _triangulate(v):
-    """ear clipping of a simple polygon (open vertex array) -> list of triangles"""
+    """ear clipping of a simple polygon (open vertex array) -> list of triangles.  The triangles must cover the
+    polygon: a remainder that cannot be clipped (self-intersecting or numerically degenerate input) raises instead of
+    being dropped -- an obstacle part that is silently not staged would be a missed collision."""
     v = np.asarray(v, dtype=np.float64)
-    area = 0.5 * np.sum(v[:, 0] * np.roll(v[:, 1], -1) - np.roll(v[:, 0], -1) * v[:, 1])
+    area = 0.5 * _area2(v)
     idx = list(range(len(v))) if area > 0 else list(range(len(v)))[::-1]
     tris = []
 
     def cross(o, a, b):
         return (a[0] - o[0]) * (b[1] - o[1]) - (a[1] - o[1]) * (b[0] - o[0])
 
-    guard = 0
-    while len(idx) > 3 and guard < 10000:
-        guard += 1
+    while len(idx) > 3:
         n = len(idx)
         for k in range(n):
             i0, i1, i2 = idx[k - 1], idx[k], idx[(k + 1) % n]
@@ -80,23 +90,46 @@ def _triangulate(v):
                 idx.pop(k)
                 break
         else:
-            break       # numerically degenerate remainder: drop it (zero area)
+            # no ear left: collinear runs are harmless (zero area), anything else is not a simple polygon
+            rest = v[idx]
+            if abs(_area2(rest)) > 1e-9 * max(abs(area), 1e-300):
+                raise ValueError("obstacle polygon cannot be triangulated (not a simple polygon?): %d vertices left "
+                                 "with area %.3g of %.3g" % (len(idx), 0.5 * abs(_area2(rest)), abs(area)))
+            idx = []
     if len(idx) == 3:
         tris.append(v[idx])
+    covered = sum(0.5 * abs(_area2(t)) for t in tris)
+    if abs(covered - abs(area)) > 1e-9 * max(abs(area), 1e-300):
+        raise ValueError("triangulation covers %.17g of the polygon's area %.17g" % (covered, abs(area)))
     return tris
+
+
+def _circle_ring(center, radius, quad_segs=16):
+    """the polygon the reference tests for a commonroad Circle: `shape.shapely_object` is Point(center).buffer(radius),
+    a ring of 4*quad_segs vertices ON the circle, clockwise from angle 0 (shapely's default quad_segs=16; GEOS
+    evaluates the same angles, last-place differences fall under the 1e-9 m policy)"""
+    k = np.arange(4 * quad_segs)
+    ang = -k * (np.pi / (2 * quad_segs))
+    return np.stack([center[0] + radius * np.cos(ang), center[1] + radius * np.sin(ang)], -1)
 
 
 def convex_pieces(shape, max_verts=8):
     """convex pieces (open vertex arrays) of a CommonRoad-like shape.  A ShapeGroup contributes its members
     (reference get_shapely_object unions them, auxiliary/collisionChecker.py:37-47; testing the members one by one is
-    equivalent), a non-convex polygon its triangles."""
+    equivalent), a non-convex polygon its triangles, a circle the fans of its 64-gon."""
     if hasattr(shape, 'shapes'):
         out = []
         for s in shape.shapes:
             out.extend(convex_pieces(s, max_verts))
         return out
     if not hasattr(shape, 'vertices'):
-        raise NotImplementedError("shape %r has no vertices (circles are not supported)" % type(shape).__name__)
+        if hasattr(shape, 'radius') and hasattr(shape, 'center'):
+            ring = _circle_ring(np.asarray(shape.center, dtype=np.float64), float(shape.radius))
+            c = np.asarray(shape.center, dtype=np.float64)[None]
+            step = max_verts - 2                   # centre + (step + 1) consecutive ring vertices per piece
+            return [np.concatenate([c, ring[np.arange(i, min(i + step, len(ring)) + 1) % len(ring)]])
+                    for i in range(0, len(ring), step)]
+        raise NotImplementedError("shape %r has neither vertices nor centre/radius" % type(shape).__name__)
     v = np.asarray(shape.vertices, dtype=np.float64)
     if len(v) > 1 and np.array_equal(v[0], v[-1]):
         v = v[:-1]
@@ -218,14 +251,9 @@ class PrimitiveChecker:
         self.backend = backend if backend is not None else get_engine('planner')
         lay = self.layout
         # the library is staged once per (engine, automaton, time step): replanning only re-stages the scene
-        key = (id(MA), float(time_step), len(MA.primitives))
-        if getattr(self.backend, '_staged_library', None) != key:
-            self.backend.upload_library(lay['verts'], lay['nv'], lay['tidx'], lay['set_off'], lay['set_idx'])
-            try:
-                self.backend._staged_library = key
-                self.backend._staged_library_ref = MA          # keeps id(MA) from being reused
-            except AttributeError:
-                pass
+        self._lib_key = (id(MA), float(time_step), len(MA.primitives))
+        self._scene_arrays = None
+        self._ensure_library()
         self.index_of = {id(p): i for i, p in enumerate(MA.primitives)}
         self._set_len = np.diff(lay['set_off'])
         self._set_len_list = [int(v) for v in self._set_len]
@@ -234,10 +262,34 @@ class PrimitiveChecker:
         self.mode = MODE_PLANNER
         self.stats = dict(queries=0, candidates=0, refined_fp64=0, near_tangent=0, exact_ties=0, pairs_nominal=0)
 
+    def _ensure_library(self):
+        be, lay = self.backend, self.layout
+        if getattr(be, '_staged_library', None) != self._lib_key:
+            be.upload_library(lay['verts'], lay['nv'], lay['tidx'], lay['set_off'], lay['set_idx'])
+            be._staged_library = self._lib_key
+            be._staged_library_ref = self.MA          # keeps id(MA) from being reused
+
     def set_scenes(self, scene_set, mode=MODE_PLANNER):
-        self.scene_arrays = scene_set.stage(self.backend)
+        self.scene_arrays = self._scene_arrays = scene_set.stage(self.backend)
+        self.backend._scene_owner = self
         self.nscenes = len(scene_set.origins)
         self.mode = mode
+
+    def _ensure_staged(self):
+        """An engine holds ONE library and ONE scene set, and several checkers (another planner call, the single-call
+        collision_check, a validator) may share the process-wide engine: before a query, whoever staged last must be
+        this checker -- otherwise its own library / scenes go back on the device first."""
+        be = self.backend
+        if getattr(be, '_staged_library', None) != self._lib_key:
+            self._ensure_library()
+            be._scene_owner = None
+        if getattr(be, '_scene_owner', None) is not self:
+            if self._scene_arrays is None:
+                raise RuntimeError("PrimitiveChecker.set_scenes has not been called")
+            a = self._scene_arrays
+            be.set_scenes(a['scene_step_off'], a['origins'], a['step_obst_off'], a['obst'], a['obst_nv'],
+                          a['step_seg_begin'], a['step_seg_end'], a['segs'])
+            be._scene_owner = self
 
     def _account(self, st, ncand):
         s = self.stats
@@ -249,6 +301,8 @@ class PrimitiveChecker:
     def bucket_collides(self, x, y, phi, t0, step_limit, bucket, scenes=(0,)):
         """collision bits (True = collides) of every primitive of velocity bucket `bucket` appended at pose
         (x, y, phi) and time index t0; with several scenes a candidate collides if it does in any of them"""
+        if getattr(self.backend, '_scene_owner', None) is not self or self.backend._staged_library != self._lib_key:
+            self._ensure_staged()
         cnt = self._set_len_list[bucket]
         ns = len(scenes)
         ent = self._qbuf.get(ns)
@@ -296,6 +350,7 @@ class PrimitiveChecker:
     def bucket_expand(self, x, y, phi, cost, t0, step_limit, bucket, scenes=(0,)):
         """bucket_collides plus the cost expand_node gives every child and the step goal_check would return for it
         (-1: goal not reached): (bits, cost, goal_step)"""
+        self._ensure_staged()
         cnt = int(self._set_len[bucket])
         ns = len(scenes)
         ent = self._qbuf.get(ns)
@@ -316,6 +371,7 @@ class PrimitiveChecker:
 
     def list_collides(self, x, y, phi, t0, step_limit, prim_indices, scenes=(0,)):
         """same for an explicit list of primitive indices"""
+        self._ensure_staged()
         idx = np.asarray(prim_indices, dtype=np.int32)
         q = make_queries(len(scenes))
         q['x'], q['y'], q['c'], q['s'] = x, y, np.cos(phi), np.sin(phi)

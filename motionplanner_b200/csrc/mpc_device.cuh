@@ -271,6 +271,20 @@ __global__ void k_stage_obst(int nslots, const double *__restrict__ src64, const
             }
             for (int k = nv; k < VB; k++) { x[k] = x[nv - 1]; y[k] = y[nv - 1]; }
         }
+        // the separating-axis test needs convex pieces (a reflex edge would "separate" what it must not): every turn
+        // to the left, one revolution in all.  Offenders are counted, mpc_set_scenes fails with MPC_E_ARG.
+        if (ok) {
+            double turn = 0.0;
+            bool reflex = false;
+            for (int k = 0; k < nv; k++) {
+                const int k1 = (k + 1 == nv) ? 0 : k + 1, k2 = (k1 + 1 == nv) ? 0 : k1 + 1;
+                const double ex = x[k1] - x[k], ey = y[k1] - y[k], fx = x[k2] - x[k1], fy = y[k2] - y[k1];
+                const double cr = ex * fy - ey * fx;
+                if (cr < -1e-12 * (fabs(ex * fy) + fabs(ey * fx)) - 1e-300) reflex = true;
+                if ((ex != 0.0 || ey != 0.0) && (fx != 0.0 || fy != 0.0)) turn += atan2(cr, ex * fx + ey * fy);
+            }
+            if (reflex || fabs(turn - 6.283185307179586) > 1e-6) atomicAdd(reinterpret_cast<int *>(maxabs) + 1, 1);
+        }
     }
     if (!ok) {
         // never near, and "always separated" for whoever tests it anyway: a point far away

@@ -187,8 +187,8 @@ extern "C" int mpc_create(int device, mpc_ctx **out) {
     CU(raise_smem_limits(ctx->prop));     // once, here: the attribute cannot be changed while a graph is being captured
     for (auto &ev : ctx->ev) CU(cudaEventCreate(&ev));
     CU(ensure(ctx, ctx->res_d, sizeof(Counters) + 4096));
-    CU(ensure(ctx, ctx->maxabs, sizeof(float)));
-    CU(cudaMemsetAsync(ctx->maxabs.p, 0, sizeof(float), ctx->stream));
+    CU(ensure(ctx, ctx->maxabs, 2 * sizeof(float)));       // [largest |coordinate| of the scenes, count of non-convex obstacle pieces]
+    CU(cudaMemsetAsync(ctx->maxabs.p, 0, 2 * sizeof(float), ctx->stream));
     ctx->wl_cap = 1 << 18;
     if (const char *e = getenv("MPC_WL_CAP")) ctx->wl_cap = std::max(1, atoi(e));      // test hook: force the overflow path
     CU(ensure(ctx, ctx->wl, sizeof(int4) * (size_t)ctx->wl_cap));
@@ -302,7 +302,16 @@ extern "C" int mpc_upload_library(mpc_ctx *ctx, const double *verts, const int32
         double x[MPC_MAX_LIB_VERTS], y[MPC_MAX_LIB_VERTS];
         if (nv > 0) {
             const double *src = verts + i * (size_t)Vmax * 2;
-            for (int k = 0; k < nv; k++) { x[k] = src[2 * k]; y[k] = src[2 * k + 1]; }
+            // repeated consecutive vertices (zero-length edges) are dropped: such an edge has no normal, its axis would
+            // report separation 0 and send every pair no other axis separates by more than tau to the tie-break pass
+            int m = 0;
+            for (int k = 0; k < nv; k++) {
+                const double vx = src[2 * k], vy = src[2 * k + 1];
+                if (m > 0 && x[m - 1] == vx && y[m - 1] == vy) continue;
+                x[m] = vx; y[m] = vy; m++;
+            }
+            while (m > 1 && x[m - 1] == x[0] && y[m - 1] == y[0]) m--;
+            nv = m >= 3 ? m : 0;
             double area = 0.0;
             for (int k = 0; k < nv; k++) {
                 int k1 = (k + 1 == nv) ? 0 : k + 1;
@@ -310,6 +319,20 @@ extern "C" int mpc_upload_library(mpc_ctx *ctx, const double *verts, const int32
             }
             if (area == 0.0) nv = 0;       // degenerate occupancy: nothing to contain
             if (area < 0.0) { std::reverse(x, x + nv); std::reverse(y, y + nv); }
+            // the separating-axis test is only correct for convex polygons: a reflex edge "separates" what it should
+            // not, an unsafe false negative.  Every turn must be to the left and the turns must add up to one revolution
+            // (a self-wrapping ring turns left all the way, twice).
+            double turn = 0.0;
+            for (int k = 0; k < nv; k++) {
+                const int k1 = (k + 1 == nv) ? 0 : k + 1, k2 = (k1 + 1 == nv) ? 0 : k1 + 1;
+                const double ex = x[k1] - x[k], ey = y[k1] - y[k], fx = x[k2] - x[k1], fy = y[k2] - y[k1];
+                const double cr = ex * fy - ey * fx, dt = ex * fx + ey * fy;
+                if (cr < -1e-12 * (std::fabs(ex * fy) + std::fabs(ey * fx)) - 1e-300)
+                    return fail(ctx, MPC_E_ARG, "occupancy %zu (primitive %zu, slot %zu) is not convex at vertex %d: decompose it into convex pieces", i, i / J, i % J, k1);
+                turn += std::atan2(cr, dt);
+            }
+            if (nv > 0 && std::fabs(turn - 6.283185307179586) > 1e-6)
+                return fail(ctx, MPC_E_ARG, "occupancy %zu (primitive %zu, slot %zu) is not a simple convex ring (total turning %.3f rad)", i, i / J, i % J, turn);
         }
         hnv[i] = nv;
         if (nv == 0) {
@@ -343,8 +366,6 @@ extern "C" int mpc_upload_library(mpc_ctx *ctx, const double *verts, const int32
         hc[i] = make_float4((float)cx, (float)cy, std::nextafter((float)rr, INFINITY), (float)nv);
         rmax = std::max(rmax, hc[i].z);
     }
-    // note: a zero-length edge keeps normal (0,0); k_check turns its line into "never separating" only for e >= nv,
-    // so give such edges the same treatment by dropping them here
     CU(ensure(ctx, ctx->lib_v, hv.size() * sizeof(float4)));
     CU(ensure(ctx, ctx->lib_n, hn.size() * sizeof(float4)));
     CU(ensure(ctx, ctx->lib_c, hc.size() * sizeof(float4)));
@@ -458,6 +479,7 @@ extern "C" int mpc_upload_library(mpc_ctx *ctx, const double *verts, const int32
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->P = P; ctx->J = J; ctx->lib_vmax = VA; ctx->VA = VA; ctx->lib_radius = radius; ctx->lib_rmax = rmax;
     ctx->lib_full = std::all_of(hnv.begin(), hnv.end(), [](int n) { return n > 0; });
+    invalidate_graphs(ctx);      // captured launches bake in what depends on the library (compaction flag, slot order, radii)
     ctx->have_lib = true;
     ctx->prepared = false;
     ctx->arena_valid = false;
@@ -596,7 +618,7 @@ static int set_scenes_impl(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_
     CU(ensure(ctx, ctx->sg_box, (size_t)(sg_stride / 8 + 1) * sizeof(float4)));
     lap("validate + ensure");
     // the small per-scene arrays travel as one packed block (one driver call instead of nine)
-    size_t meta_bytes = 0, m_org = 0, m_sg = 0, m_sso = 0, m_ss = 0;
+    size_t meta_bytes = 0, m_org = 0, m_sg = 0, m_sso = 0, m_ss = 0, m_flag = 0;
     bool use_seg_dev = false;
     {
         const size_t n_org = (size_t)nscenes * 2 * sizeof(double), n_sg = (size_t)sg_stride * 4 * sizeof(double);
@@ -606,6 +628,7 @@ static int set_scenes_impl(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_
         auto take = [&](size_t n) { size_t o = off; off += (n + 15) / 16 * 16; return o; };
         const size_t o_org = take(n_org), o_sg = take(n_sg), o_sso = take(n_sso), o_slot = take(n_st1), o_src = take(n_st1),
                      o_cnt = take(n_st), o_sb = take(n_st), o_se = take(n_st), o_ss = take(n_ss);
+        const size_t o_flag = take(16);                    // host side only: what the staging kernels report back
         if (off > ctx->h_meta_cap) {
             if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
             ctx->h_meta = nullptr;
@@ -667,7 +690,7 @@ static int set_scenes_impl(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_
         ctx->step_seg_begin.p = d + o_sb; ctx->step_seg_end.p = d + o_se; ctx->seg_scene.p = d + o_ss;
         // captured graphs hold these addresses: a different layout is a different graph
         ctx->meta_sig = (long long)(o_sg * 1315423911ull ^ o_sso * 2654435761ull ^ o_slot * 40503ull ^ o_ss * 97ull ^ off);
-        meta_bytes = off; m_org = o_org; m_sg = o_sg; m_sso = o_sso; m_ss = o_ss;
+        meta_bytes = off; m_org = o_org; m_sg = o_sg; m_sso = o_sso; m_ss = o_ss; m_flag = o_flag;
         use_seg_dev = seg_dev;
     }
     // everything that goes to the stream after the host-side passes
@@ -690,7 +713,7 @@ static int set_scenes_impl(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_
                 CU(cudaGetLastError());
             }
         }
-        CU(cudaMemsetAsync(ctx->maxabs.p, 0, sizeof(float), st));
+        CU(cudaMemsetAsync(ctx->maxabs.p, 0, 2 * sizeof(float), st));
         if (nobst) {
             int blocks = (noslots + 127) / 128;
             if (VB == 4) {
@@ -717,6 +740,7 @@ static int set_scenes_impl(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_
                                                              (float4 *)ctx->sg_f.p, sg_stride, (float4 *)ctx->sg_box.p, (float *)ctx->maxabs.p);
             CU(cudaGetLastError());
         }
+        CU(cudaMemcpyAsync(h + m_flag, ctx->maxabs.p, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
         return MPC_OK;
     };
     if (!use_graph) {
@@ -752,6 +776,14 @@ static int set_scenes_impl(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_
     lap("enqueue copies+kernels");
     CU(cudaStreamSynchronize(st));
     lap("device sync");      // host buffers (incl. the local staging vectors) may be reused after return
+    {
+        const int bad = ((const int *)((const char *)ctx->h_meta + m_flag))[1];
+        if (bad > 0) {
+            ctx->have_scenes = false;
+            return fail(ctx, MPC_E_ARG, "%d obstacle piece(s) are not convex: decompose them before staging (the separating-axis test "
+                                        "would report false separations)", bad);
+        }
+    }
     ctx->nscenes = nscenes; ctx->nsteps = nsteps; ctx->nobst = nobst; ctx->nseg = nslots; ctx->sg_stride = sg_stride;
     ctx->ob_stride = ob_stride;
     ctx->ob_vmax = VB; ctx->VB = VB; ctx->max_obst_step = max_o; ctx->max_seg_step = max_s;

@@ -59,6 +59,7 @@ class CollisionEngine:
             raise MpcError("mpc_create(device=%d) -> %d: %s" % (device, rc, msg))
         self.device = int(device)
         self._keep = {}
+        self._staged_library = self._scene_owner = None
 
     def close(self):
         if getattr(self, "_ctx", None):
@@ -147,6 +148,7 @@ class CollisionEngine:
                 _cabi.ptr(segs), len(segs), keep)
 
     def set_scenes_args(self, args):
+        self._scene_owner = None             # whoever staged through a PrimitiveChecker sets it again after this call
         rc = self._L.mpc_set_scenes(self._ctx, *args[:11])
         if rc != 0:
             self._check(rc, "mpc_set_scenes")

@@ -26,6 +26,12 @@ PLANNER = 'AutomatonStandalone'
 def solve_scenario(path, MA, max_nodes=20000, backend=None, validator=None):
     """one row of the result table (reference solve_scenario :37-108)"""
     scenario, planning_problem = CommonRoadFileReader(path).open(lanelet_assignment=True)
+    return solve_loaded(os.path.basename(path), scenario, planning_problem, MA, max_nodes, backend, validator)[0]
+
+
+def solve_loaded(file, scenario, planning_problem, MA, max_nodes=20000, backend=None, validator=None):
+    """solve_scenario for an already parsed scenario; returns (row, x, u, param)"""
+    x = u = None
     pp = list(planning_problem.planning_problem_dict.values())[0]
     steps = 0
     for g in pp.goal.state_list:
@@ -48,7 +54,7 @@ def solve_scenario(path, MA, max_nodes=20000, backend=None, validator=None):
                 collision = 'collision'
     except Exception as e:          # same convention as the reference: the message goes into the table
         comp_time = str(e).replace("\n", "").replace(",", "")
-    return [os.path.basename(path), comp_time, collision, tags, final_time]
+    return [file, comp_time, collision, tags, final_time], x, u, param
 
 
 def run_all(scenario_dir, results_dir='results', max_nodes=20000, files=None, backend=None, validator=None):

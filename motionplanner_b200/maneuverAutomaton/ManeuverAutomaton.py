@@ -1,8 +1,25 @@
 """Maneuver-automaton data model -- same public attributes as reference maneuverAutomaton/ManeuverAutomaton.py:3-44,
 plus the flat array view (`device_layout`) that is staged once in HBM (include/mpc.h: mpc_upload_library)."""
+import weakref
+
 import numpy as np
 
 from ..geometry import polygon_vertices
+
+# id(primitive) -> (weak reference to its automaton, index): lets the module-level collision_check(node, primitive, ...)
+# of the planners find the staged library from the primitive alone, as the reference's signature demands
+# (src/lowLevelPlannerManeuverAutomaton.py:95), without anything being planted in `param`
+_PRIMITIVE_OWNER = {}
+
+
+def automaton_of(primitive):
+    """(automaton, index of `primitive` in automaton.primitives) for a primitive of a live ManeuverAutomaton"""
+    hit = _PRIMITIVE_OWNER.get(id(primitive))
+    MA = hit[0]() if hit is not None else None
+    if MA is None or hit[1] >= len(MA.primitives) or MA.primitives[hit[1]] is not primitive:
+        raise KeyError("motion primitive does not belong to a ManeuverAutomaton of this package (build the automaton "
+                       "with motionplanner_b200.maneuverAutomaton.ManeuverAutomaton.ManeuverAutomaton)")
+    return MA, hit[1]
 
 
 def _fast_vertices(geom):
@@ -47,6 +64,17 @@ class ManeuverAutomaton:
         for p in self.primitives:
             p.successors = self.velocity2primitives(p.x[2, -1])
         self._layouts = {}
+        self._register()
+
+    def _register(self):
+        def forget(dead, ids=[id(p) for p in self.primitives]):
+            for i in ids:
+                if _PRIMITIVE_OWNER.get(i, (None,))[0] is dead:
+                    del _PRIMITIVE_OWNER[i]
+
+        ref = weakref.ref(self, forget)
+        for i, p in enumerate(self.primitives):
+            _PRIMITIVE_OWNER[id(p)] = (ref, i)
 
     def _bucket(self, v):
         return np.round(v / self.v_diff).astype(int)
@@ -64,6 +92,7 @@ class ManeuverAutomaton:
     def __setstate__(self, d):
         self.__dict__.update(d)
         self._layouts = {}
+        self._register()
 
     def bucket_stacks(self, bucket):
         """reference trajectories of a velocity bucket stacked by length: [(positions in the bucket, [m, 4, L])];

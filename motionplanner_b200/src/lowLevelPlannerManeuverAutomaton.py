@@ -20,6 +20,7 @@ import numpy as np
 from ..checker import PrimitiveChecker, SceneSet
 from ..geometry import Point
 from ..maneuverAutomaton.Controller import FeedbackController
+from ..maneuverAutomaton.ManeuverAutomaton import automaton_of
 
 
 _COST = operator.attrgetter('cost')      # stable sort key of the search queue (reference :54)
@@ -81,17 +82,24 @@ def _time_exceeded(ind, goals):
 
 
 def collision_check(node, primitive, space, param, timepoint, checker=None):
-    """check if a motion primitive is collision free (True = free) -- single-primitive form of the reference call
-    (:95-125).  `space` is the list of free-space geometries; pass `checker` to reuse staged data."""
+    """check if a motion primitive is collision free (True = free) -- the reference's call (:95-125) with the
+    reference's arguments: `node` needs `.x` only (a reference `Node` works; nodes of the batched search also carry
+    the bit decided at expansion), `primitive` is a primitive of a ManeuverAutomaton of this package, `space` the
+    list of free-space geometries, `param` the reference's dictionary ('goal', 'steps', 'time_step'; nothing is
+    added to it).  `checker` (extension) reuses staged data; without it the automaton is found through the primitive
+    and (automaton, space) are staged once and cached."""
     ind = node.x.shape[1] - primitive.x.shape[1]
     if _time_exceeded(ind, param['goal']):
         return False
-    if node.collides is not None:
-        return not node.collides
+    bit = getattr(node, 'collides', None)
+    if bit is not None:
+        return not bit
     if checker is None:
-        checker = _checker_for(param['_MA'], param['time_step'], space, timepoint)
+        MA, idx = automaton_of(primitive)
+        checker = _checker_for(MA, param['time_step'], space, timepoint)
+    else:
+        idx = checker.index_of[id(primitive)]
     x = node.x[:, ind]
-    idx = checker.index_of[id(primitive)]
     scenes = (0,) if timepoint else (0, 1)
     return not bool(checker.list_collides(x[0], x[1], x[3], ind, param['steps'], [idx], scenes)[0])
 
@@ -100,8 +108,10 @@ _CACHE = {}
 
 
 def _checker_for(MA, time_step, space, timepoint, backend=None):
-    """stage automaton + free space once per (automaton, space list) pair"""
-    key = (id(MA), float(time_step), id(space), bool(timepoint), id(backend))
+    """stage automaton + free space once per (automaton, space list) pair.  The key holds the identity of every
+    geometry of the list (a list mutated in place is a different free space); the checker itself re-stages its scenes
+    when another user of the engine has staged in between (PrimitiveChecker._ensure_staged)."""
+    key = (id(MA), float(time_step), id(space), tuple(map(id, space)), bool(timepoint), id(backend))
     hit = _CACHE.get('k')
     if hit is not None and hit[0] == key and hit[1] is space:
         return hit[2]
@@ -115,7 +125,7 @@ def _checker_for(MA, time_step, space, timepoint, backend=None):
         scenes.add_scene_from_spaces(space[:-1])
         scenes.add_scene_from_spaces(space[1:])
     chk.set_scenes(scenes)
-    _CACHE['k'] = (key, space, chk)
+    _CACHE['k'] = (key, space, chk, list(space))        # the last entry keeps the geometries (their ids) alive
     return chk
 
 
@@ -210,7 +220,6 @@ def lowLevelPlannerManeuverAutomaton(scenario, planning_problem, param, space_al
     if device_expand:
         checker.enable_expand(ref_traj, param['goal'], param['b'])
     scenes = (0,) if timepoint else (0, 1)
-    param['_MA'] = MA
 
     # initial state, shifted from the vehicle centre to the rear axle (:33-36)
     x = np.expand_dims(np.array([param['x0'][0], param['x0'][1], param['v_init'], param['orientation']]), 1)

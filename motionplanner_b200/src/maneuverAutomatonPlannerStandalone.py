@@ -11,7 +11,7 @@ boundary as segments plus the obstacle pieces of every step -- which is what the
 """
 from copy import deepcopy
 
-import operator
+import heapq
 
 import numpy as np
 
@@ -19,10 +19,8 @@ from ..auxiliary.polygonLaneletNetwork import polygonLaneletNetwork
 from ..checker import PrimitiveChecker, SceneSet, scenario_obstacle_arrays
 from ..geometry import Point
 from ..maneuverAutomaton.Controller import FeedbackController
+from ..maneuverAutomaton.ManeuverAutomaton import automaton_of
 from .lowLevelPlannerManeuverAutomaton import (Node, _rotation, extract_control_inputs, transform_trajectory)
-
-
-_COST = operator.attrgetter('cost')      # stable sort key of the search queue (reference :54)
 
 
 class FreeSpace:
@@ -114,28 +112,54 @@ def free_space(scenario, goal_set, x0):
 def _stage(MA, space, param, backend=None):
     chk = PrimitiveChecker(MA, param['time_step'], backend)
     scenes = SceneSet()
-    if param['timepoint']:
-        n, off, obst, nv = space.scene_set()
-        scenes.add_scene_explicit(n, off, obst, nv, space.road.segments, origin=space.origin)
-    else:   # interval occupancies: inside space[i] n space[i+1]  <=>  inside both (reference :38-43)
-        for shift in (0, 1):
-            n, off, obst, nv = space.scene_set(drop_last=1, shift=shift)
+    if hasattr(space, 'scene_set'):                 # FreeSpace handle of this module's free_space()
+        if param['timepoint']:
+            n, off, obst, nv = space.scene_set()
             scenes.add_scene_explicit(n, off, obst, nv, space.road.segments, origin=space.origin)
+        else:   # interval occupancies: inside space[i] n space[i+1]  <=>  inside both (reference :38-43)
+            for shift in (0, 1):
+                n, off, obst, nv = space.scene_set(drop_last=1, shift=shift)
+                scenes.add_scene_explicit(n, off, obst, nv, space.road.segments, origin=space.origin)
+    else:                                           # the reference's list of shapely(-like) polygons, one per step;
+        scenes.add_scene_from_spaces(space)         # for interval automata the reference has intersected them already
     chk.set_scenes(scenes)
     return chk
 
 
+_CACHE = {}
+
+
+def _checker_for(MA, space, param):
+    """single-call collision_check: automaton + free space staged once per (automaton, space) pair"""
+    key = (id(MA), float(param['time_step']), id(space), bool(param['timepoint']))
+    hit = _CACHE.get('k')
+    if hit is not None and hit[0] == key and hit[1] is space:
+        return hit[2]
+    chk = _stage(MA, space, param)
+    _CACHE['k'] = (key, space, chk)
+    return chk
+
+
 def collision_check(node, primitive, space, goal_set, param, checker=None):
-    """check if a motion primitive is collision free (reference :196-226); uses the bit attached at expansion"""
+    """check if a motion primitive is collision free (reference :196-226), called with the reference's arguments:
+    `node` needs `.x` only, `space` is the FreeSpace handle of free_space() or a list of shapely-like polygons, `param`
+    carries 'timepoint', 'steps', 'time_step' as the reference's planner sets them (:34-36).  Nodes of the batched
+    search carry the bit decided at expansion."""
     ind = node.x.shape[1] - primitive.x.shape[1]
     if all(ind > g['time_end'] for g in goal_set):
         return False
-    if node.collides is not None:
-        return not node.collides
-    checker = checker if checker is not None else _stage(param['_MA'], space, param)
+    bit = getattr(node, 'collides', None)
+    if bit is not None:
+        return not bit
+    if checker is None:
+        MA, idx = automaton_of(primitive)
+        checker = _checker_for(MA, space, param)
+    else:
+        idx = checker.index_of[id(primitive)]
     x = node.x[:, ind]
-    scenes = (0,) if param['timepoint'] else (0, 1)
-    return not bool(checker.list_collides(x[0], x[1], x[3], ind, param['steps'], [checker.index_of[id(primitive)]], scenes)[0])
+    # a FreeSpace staged for an interval automaton is two shifted scenes; a list of polygons is used as it is
+    scenes = (0,) if param['timepoint'] or not hasattr(space, 'scene_set') else (0, 1)
+    return not bool(checker.list_collides(x[0], x[1], x[3], ind, param['steps'], [idx], scenes)[0])
 
 
 def goal_check(node, primitive, goal_set, param):
@@ -163,8 +187,23 @@ def expand_node(node, primitive, ind, T, goal_set, collides=None):
     return Node(primitives, x, cost, collides)
 
 
-def _children(checker, node, MA, bucket, goal_set, param):
-    ind = node.x.shape[1] - 1
+def _goal_rings(goal_set):
+    """(a, b - a, max(|b - a|^2, 1e-300)) edge arrays of every goal's exterior ring, as `_Ring.distance` uses them"""
+    out = []
+    for goal in goal_set:
+        if goal['space'] is not None:
+            c = np.asarray(goal['space'].exterior.coords, dtype=np.float64).reshape(-1, 2)
+            a, d = c[:-1], c[1:] - c[:-1]
+            out.append((a, d, np.maximum(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1], 1e-300)))
+    return out
+
+
+def _children(checker, node, MA, bucket, goal_set, param, rings=None):
+    """all children of `node` (one velocity bucket): one device query for the collision bits, one batched product for
+    the trajectories, one vectorised pass for the costs.  Per child the arithmetic is that of expand_node (reference
+    :293-310) -- tests/test_planner.py asserts bit equality -- and trajectories are assembled when a child is popped."""
+    x = node.x
+    ind = x.shape[1] - 1
     cand = MA.vel_dic[bucket]
     if not cand:
         return []
@@ -172,9 +211,28 @@ def _children(checker, node, MA, bucket, goal_set, param):
     if all(ind > g['time_end'] for g in goal_set):
         bits = np.ones(len(cand), bool)
     else:
-        bits = checker.bucket_collides(node.x[0, -1], node.x[1, -1], node.x[3, -1], ind, param['steps'], bucket, scenes)
-    T = _rotation(node.x[3, -1])
-    return [expand_node(node, MA.primitives[i], i, T, goal_set, bool(b)) for i, b in zip(cand, bits)]
+        bits = checker.bucket_collides(x[0, -1], x[1, -1], x[3, -1], ind, param['steps'], bucket, scenes)
+    if rings is None:
+        rings = _goal_rings(goal_set)
+    T = _rotation(x[3, -1])
+    off = np.array([[x[0, -1]], [x[1, -1]], [0], [x[3, -1]]])
+    costs = np.full(len(cand), np.inf)
+    segs = [None] * len(cand)
+    for loc, PX in MA.bucket_stacks(bucket):
+        X = T @ PX + off                                           # [m, 4, L]
+        # the reference's loop starts at node.x.shape[1] + 1, i.e. at state 2 of the appended primitive (:304)
+        px, py = X[:, 0, 2:, None], X[:, 1, 2:, None]              # [m, L-2, 1]
+        if px.shape[1]:
+            for a, d, l2 in rings:
+                t = np.clip(((px - a[:, 0]) * d[:, 0] + (py - a[:, 1]) * d[:, 1]) / l2, 0.0, 1.0)
+                qx, qy = a[:, 0] + t * d[:, 0], a[:, 1] + t * d[:, 1]
+                dist = np.sqrt((qx - px) ** 2 + (qy - py) ** 2)
+                costs[loc] = np.minimum(costs[loc], dist.reshape(len(loc), -1).min(axis=1))
+        for k, i in enumerate(loc):
+            segs[i] = X[k]
+    base = node.primitives
+    return [Node(base + [i], None, c, b, node, seg)
+            for i, c, b, seg in zip(cand, costs.tolist(), bits.tolist(), segs)]
 
 
 def maneuverAutomatonPlannerStandalone(scenario, planning_problem, param, MA, backend=None, max_nodes=None):
@@ -189,21 +247,27 @@ def maneuverAutomatonPlannerStandalone(scenario, planning_problem, param, MA, ba
     param['timepoint'] = MA.is_timepoint()
     param['steps'] = len(space)
     param['time_step'] = scenario.dt
-    param['_MA'] = MA
-    if not param['timepoint']:
-        param['_space_len'] = len(space) - 1
     checker = _stage(MA, space, param, backend)
 
     x = np.expand_dims(x0, axis=1)
     x[0, 0] = x[0, 0] - np.cos(x[3, 0]) * param['b']
     x[1, 0] = x[1, 0] - np.sin(x[3, 0]) * param['b']
 
+    # The reference keeps a list, sorts it (stably) by cost at every iteration and pops the head (:62-64).  Costs are
+    # never changed after insertion here, so the list is always ordered by (cost, insertion number) and its head is the
+    # minimum of that pair: a binary heap on (cost, insertion number) pops the very same nodes in the same order
+    # (tests/test_planner.py::test_heap_pops_like_stable_sort) without re-sorting 10^5 entries per popped node.
     node = Node([], x, 0)
-    queue = _children(checker, node, MA, int(MA._bucket(x0[2])), goal_set, param)
+    rings = _goal_rings(goal_set)
+    seq = 0
+    queue = []
+    for child in _children(checker, node, MA, int(MA._bucket(x0[2])), goal_set, param, rings):
+        queue.append((child.cost, seq, child))
+        seq += 1
+    heapq.heapify(queue)
     popped = 0
     while len(queue) > 0:
-        queue.sort(key=_COST)
-        node = queue.pop(0)
+        node = heapq.heappop(queue)[2]
         popped += 1
         if max_nodes is not None and popped > max_nodes:
             break
@@ -218,5 +282,7 @@ def maneuverAutomatonPlannerStandalone(scenario, planning_problem, param, MA, ba
                 K = [np.zeros([u.shape[0], x.shape[0]]) for _ in range(u.shape[1])]
                 controller = FeedbackController(x, u, t, K)
                 return transform_trajectory(node.x[:, :ind + 1], param), u[:, :ind], controller
-            queue.extend(_children(checker, node, MA, int(MA._bucket(primitive.x[2, -1])), goal_set, param))
+            for child in _children(checker, node, MA, int(MA._bucket(primitive.x[2, -1])), goal_set, param, rings):
+                heapq.heappush(queue, (child.cost, seq, child))
+                seq += 1
     return None, None, None

@@ -130,9 +130,13 @@ def c4_problem(P=4096, O_lanes=8, slots=32, T=50, nqueries=1):
 # ---------------------------------------------------------------------------------------------------------------------
 
 def random_convex(rng, n, radius):
+    """n points in convex position: on a randomly oriented ellipse (semi-axes radius, 0.6..1 radius) at sorted angles"""
     ang = np.sort(rng.uniform(0, 2 * np.pi, n))
-    r = radius * rng.uniform(0.6, 1.0, n)
-    return np.stack([r * np.cos(ang), r * np.sin(ang)], -1)
+    while np.min(np.diff(np.concatenate([ang, [ang[0] + 2 * np.pi]]))) < 0.05:      # no near-duplicate vertices
+        ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+    a, b, rot = radius, radius * rng.uniform(0.6, 1.0), rng.uniform(0, np.pi)
+    x, y = a * np.cos(ang), b * np.sin(ang)
+    return np.stack([np.cos(rot) * x - np.sin(rot) * y, np.sin(rot) * x + np.cos(rot) * y], -1)
 
 
 def adversarial_problem(seed, P=96, J=5, nsteps=8, max_obst=10, lib_verts=4, obst_verts=4, offset=(0.0, 0.0),

@@ -18,12 +18,14 @@ class OracleBackend:
     def __init__(self):
         self.lib = self.sc = None
         self.log = []          # (queries, cand, mode, bits) of every call
+        self._staged_library = self._scene_owner = None
 
     def upload_library(self, verts, nv, tidx, set_off=None, set_idx=None):
         self.lib = dict(verts=np.array(verts, np.float64), nv=np.array(nv, np.int32), tidx=np.array(tidx, np.int32),
                         set_off=None if set_off is None else np.array(set_off, np.int32),
                         set_idx=None if set_idx is None else np.array(set_idx, np.int32))
         self.pb = None
+        self._staged_library = None
 
     def set_scenes(self, scene_step_off, origins, step_obst_off, obst, obst_nv, step_seg_begin, step_seg_end, segs):
         obst = np.asarray(obst, np.float64)
@@ -32,6 +34,7 @@ class OracleBackend:
         self.sc = dict(scene_step_off=scene_step_off, step_obst_off=step_obst_off, obst=obst, obst_nv=obst_nv,
                        step_seg_begin=step_seg_begin, step_seg_end=step_seg_end, segs=segs)
         self.pb = None
+        self._scene_owner = None
 
     def query(self, queries, cand_idx=None, mode=0):
         if self.pb is None:

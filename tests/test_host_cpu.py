@@ -184,3 +184,45 @@ def test_scene_args_marshalling_without_a_device():
     none = dict(scene, obst=None, obst_nv=None, step_obst_off=np.zeros_like(sc["step_obst_off"]))
     a2 = CollisionEngine.scene_args(*[none[k] for k in keys])
     assert a2[4] is None and a2[5] is None                           # no obstacles: null pointers, as the ABI allows
+
+
+def test_convexity_test_rejects_self_wrapping_rings_and_triangulation_covers():
+    """`_is_convex` must not accept a ring that turns one way but wraps twice; `_triangulate` must cover the
+    polygon or raise -- never drop a part of an obstacle silently"""
+    from motionplanner_b200.checker import _is_convex, _triangulate, convex_pieces
+    sq = np.array([[0, 0], [2, 0], [2, 2], [0, 2.0]])
+    assert _is_convex(sq) and _is_convex(sq[::-1])
+    star = np.array([[np.cos(a), np.sin(a)] for a in np.arange(5) * (4 * np.pi / 5)])      # pentagram: turns left, twice round
+    assert not _is_convex(star)
+    L = np.array([[0, 0], [3, 0], [3, 1], [1, 1], [1, 3], [0, 3.0]])
+    tris = _triangulate(L)
+    area = sum(0.5 * abs((t[1, 0] - t[0, 0]) * (t[2, 1] - t[0, 1]) - (t[1, 1] - t[0, 1]) * (t[2, 0] - t[0, 0])) for t in tris)
+    assert abs(area - 5.0) < 1e-12
+    bow = np.array([[0, 0], [2, 2], [2, 0], [0, 2.0]])                                      # self-intersecting
+    with pytest.raises(ValueError):
+        _triangulate(bow)
+
+    class Circle:
+        center, radius = np.array([3.0, -1.0]), 2.0
+
+    pieces = convex_pieces(Circle())
+    assert all(len(p) <= 8 and _is_convex(p) for p in pieces)
+    area = sum(0.5 * abs(np.sum(p[:, 0] * np.roll(p[:, 1], -1) - np.roll(p[:, 0], -1) * p[:, 1])) for p in pieces)
+    assert abs(area - 0.5 * 64 * 4.0 * np.sin(2 * np.pi / 64)) < 1e-12                      # area of the inscribed 64-gon
+
+
+def test_primitive_registry_finds_the_automaton():
+    from motionplanner_b200.maneuverAutomaton.ManeuverAutomaton import (ManeuverAutomaton, MotionPrimitive,
+                                                                        automaton_of)
+    prims = []
+    for i in range(6):
+        x = np.zeros((4, 11))
+        x[2] = 2.0 if i < 3 else 2.4
+        prims.append(MotionPrimitive(x, np.zeros(2), 1.0, occupancy=[{'space': None, 'time': 0.0}]))
+    MA = ManeuverAutomaton(prims)
+    assert automaton_of(prims[4]) == (MA, 4)
+    import pickle
+    MA2 = pickle.loads(pickle.dumps(MA))
+    assert automaton_of(MA2.primitives[2]) == (MA2, 2)
+    with pytest.raises(KeyError):
+        automaton_of(MotionPrimitive(np.zeros((4, 11)), np.zeros(2), 1.0))

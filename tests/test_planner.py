@@ -2,6 +2,8 @@
 signature: corridor given as one free-space polygon per time step (with a hole where an obstacle was subtracted),
 reference trajectory, the regenerated automaton.  CPU: the oracle stands in for the engine; GPU: the product engine
 must produce the identical plan, decision by decision."""
+import os
+
 import numpy as np
 import pytest
 
@@ -82,7 +84,6 @@ def test_collision_check_single_call_matches_batched(MA):
     be = OracleBackend()
     LL._CACHE.clear()
     chk = LL._checker_for(MA, 0.1, space, True, be)
-    param['_MA'] = MA
     x = np.array([[0.0 - 1.15], [0.0], [10.0], [0.0]])
     root = LL.Node([], x, 0)
     bucket = int(MA._bucket(10.0))
@@ -91,6 +92,33 @@ def test_collision_check_single_call_matches_batched(MA):
         prim = MA.primitives[k.primitives[-1]]
         lazy = LL.Node(k.primitives, k.x, k.cost, None)
         assert LL.collision_check(lazy, prim, space, param, True, chk) == (not k.collides)
+    # the reference's own call shape: a node with `primitives, x, cost` only (reference Node :217-225), no checker,
+    # nothing planted in `param` -- the automaton is found through the primitive, (automaton, space) staged once
+    class RefNode:
+        def __init__(self, primitives, x, cost):
+            self.primitives, self.x, self.cost = primitives, x, cost
+
+    import motionplanner_b200.checker as CK
+    keys_before = set(param)
+    old = CK._ENGINES.copy()
+    CK._ENGINES[('planner', int(os.environ.get('MPC_DEVICE', os.environ.get('LOCAL_RANK', '0'))))] = be
+    try:
+        LL._CACHE.clear()
+        for k in kids[::23]:
+            prim = MA.primitives[k.primitives[-1]]
+            assert LL.collision_check(RefNode(k.primitives, k.x, k.cost), prim, space, param, True) == (not k.collides)
+        staged = LL._CACHE['k'][2]
+        # another user of the same engine stages something else in between: the cached checker must notice
+        other = LL._checker_for(MA, 0.1, space[:5], True, be)
+        assert other is not staged and be._scene_owner is other
+        k = kids[3]
+        assert LL.collision_check(RefNode(k.primitives, k.x, k.cost), MA.primitives[k.primitives[-1]], space, param, True,
+                                  staged) == (not k.collides)
+        assert be._scene_owner is staged
+    finally:
+        CK._ENGINES.clear()
+        CK._ENGINES.update(old)
+    assert set(param) == keys_before
     # time guard (reference :99-109): a node whose parent index lies beyond every goal's time_end is rejected
     late = LL.Node([kids[0].primitives[-1]], np.zeros((4, 61)), 0.0, False)
     assert LL.collision_check(late, MA.primitives[kids[0].primitives[-1]], space, param, True, chk) is False
@@ -113,7 +141,6 @@ def test_planner_gpu_identical_plan(MA):
 # ---------------------------------------------------------------------------------------------------------------------
 # stand-alone planner (reference src/maneuverAutomatonPlannerStandalone.py) on a bundled scenario with a goal region
 # ---------------------------------------------------------------------------------------------------------------------
-import os  # noqa: E402
 
 REF_SCENARIOS = '/root/reference/scenarios'
 
@@ -239,6 +266,85 @@ def plan_standalone(MA, name, max_nodes, backend):
     param = vehicleParameter()
     x, u, _ = maneuverAutomatonPlannerStandalone(scenario, pps, param, MA, backend=backend, max_nodes=max_nodes)
     return scenario, param, x, u
+
+
+def test_standalone_batched_children_equal_expand_node(MA):
+    """the vectorised child construction of the stand-alone planner reproduces its expand_node (reference
+    src/maneuverAutomatonPlannerStandalone.py:293-310) bit for bit: trajectories and goal-distance costs"""
+    from motionplanner_b200.src import maneuverAutomatonPlannerStandalone as SA
+    scenario, pps = unit_scenario("ZAM_Zip-1_19_T-1")
+    pp = list(pps.planning_problem_dict.values())[0]
+    goals = SA.get_goal_set(scenario, pp)
+    assert any(g['space'] is not None for g in goals)
+
+    class AllFree:
+        def bucket_collides(self, x, y, phi, t0, limit, bucket, scenes):
+            return np.zeros(len(MA.vel_dic[bucket]), bool)
+
+    param = {'timepoint': True, 'steps': 86}
+    s0 = pp.initial_state
+    x = np.array([[s0.position[0] - 1.15], [s0.position[1]], [s0.velocity], [s0.orientation + 0.1]])
+    root = SA.Node([], x, 0)
+    for parent in (root, SA._children(AllFree(), root, MA, int(MA._bucket(s0.velocity)), goals, param)[5]):
+        bucket = int(MA._bucket(parent.x[2, -1]))
+        kids = SA._children(AllFree(), parent, MA, bucket, goals, param)
+        T = SA._rotation(parent.x[3, -1])
+        assert len(kids) == len(MA.vel_dic[bucket]) > 50
+        for k, i in list(zip(kids, MA.vel_dic[bucket]))[::7]:
+            one = SA.expand_node(parent, MA.primitives[i], i, T, goals)
+            assert k.primitives == one.primitives and k.cost == one.cost and np.isfinite(k.cost)
+            assert np.array_equal(k.x, one.x)
+
+
+def test_standalone_collision_check_with_reference_shaped_arguments(MA):
+    """stand-alone twin collision_check(node, primitive, space, goal_set, param) (reference
+    src/maneuverAutomatonPlannerStandalone.py:196-226) called the way the reference calls it: a node with
+    `primitives, x, cost` only, `space` = list of polygons, `param` with the keys the reference's planner sets"""
+    import motionplanner_b200.checker as CK
+    from motionplanner_b200.src import maneuverAutomatonPlannerStandalone as SA
+    prm, space, ref = corridor_problem(blocked=True)
+    param = {'timepoint': True, 'steps': len(space), 'time_step': 0.1, 'b': prm['b']}
+    goal_set = [{'time_start': 30, 'time_end': 40, 'space': None, 'lane': None}]
+
+    class RefNode:
+        def __init__(self, primitives, x, cost):
+            self.primitives, self.x, self.cost = primitives, x, cost
+
+    be = OracleBackend()
+    old = CK._ENGINES.copy()
+    CK._ENGINES[('planner', int(os.environ.get('MPC_DEVICE', os.environ.get('LOCAL_RANK', '0'))))] = be
+    try:
+        SA._CACHE.clear()
+        x = np.array([[0.0 - 1.15], [0.0], [10.0], [0.0]])
+        bucket = int(MA._bucket(10.0))
+        chk = LL._checker_for(MA, 0.1, space, True, be)
+        want = chk.bucket_collides(x[0, 0], x[1, 0], x[3, 0], 0, len(space), bucket)
+        assert 0 < want.sum() < len(want)
+        T = SA._rotation(0.0)
+        for k, i in list(enumerate(MA.vel_dic[bucket]))[::19]:
+            node = SA.expand_node(SA.Node([], x, 0), MA.primitives[i], i, T, goal_set)
+            got = SA.collision_check(RefNode(node.primitives, node.x, node.cost), MA.primitives[i], space, goal_set, param)
+            assert got == (not want[k])
+        assert set(param) == {'timepoint', 'steps', 'time_step', 'b'}
+    finally:
+        CK._ENGINES.clear()
+        CK._ENGINES.update(old)
+
+
+def test_heap_pops_like_stable_sort():
+    """the stand-alone planner's heap on (cost, insertion number) pops what the reference's `queue.sort(key=cost);
+    queue.pop(0)` pops (src/maneuverAutomatonPlannerStandalone.py:62-64), ties (inf costs are common) included"""
+    import heapq
+    rng = np.random.default_rng(0)
+    ref, heap, seq = [], [], 0
+    for it in range(300):
+        for c in rng.choice([np.inf, 1.0, 2.5, 2.5, 7.0, float(rng.uniform(0, 9))], size=int(rng.integers(0, 6))):
+            ref.append((float(c), seq))
+            heapq.heappush(heap, (float(c), seq))
+            seq += 1
+        if ref:
+            ref.sort(key=lambda e: e[0])
+            assert ref.pop(0) == heapq.heappop(heap)
 
 
 def test_unit_scenario_fixture_plans_on_cpu(MA):

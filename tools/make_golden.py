@@ -12,7 +12,9 @@ Also writes tests/golden/unit_scenarios.pkl.gz: three of the scenarios the refer
 (unitTests/unitTest.py:35-38), parsed by this package's reader and pickled as crlite objects, so that the whole planner
 (not only single queries) can run on the GPU box.
 
-Run from the repository root:  python tools/make_golden.py
+Also (argument `all`) tests/golden/all_scenarios.pkl.xz: every bundled scenario as crlite objects.
+
+Run from the repository root:  python tools/make_golden.py [npz|unit|all]
 """
 import glob
 import gzip
@@ -81,7 +83,23 @@ def unit_scenarios(src='/root/reference/scenarios', dst=os.path.join(ROOT, 'test
     print('wrote', dst, os.path.getsize(dst) / 1e3, 'kB')
 
 
+def all_scenarios(src='/root/reference/scenarios', dst=os.path.join(ROOT, 'tests', 'golden', 'all_scenarios.pkl.xz')):
+    """all bundled scenarios as crlite objects (scenario, planning problem set), for whole-planner runs on the GPU box
+    (BASELINE.json configs[1]; tests/test_all_scenarios_gpu.py)"""
+    import lzma
+    out = {}
+    for f in sorted(glob.glob(os.path.join(src, '*.xml'))):
+        out[os.path.basename(f)[:-4]] = CommonRoadFileReader(f).open(lanelet_assignment=True)
+    with open(dst, 'wb') as f:
+        f.write(lzma.compress(pickle.dumps(out, protocol=4), preset=6))
+    print('wrote', dst, len(out), 'scenarios', os.path.getsize(dst) / 1e6, 'MB')
+
+
 if __name__ == '__main__':
-    if len(sys.argv) < 2 or sys.argv[1] != 'unit':
+    what = sys.argv[1] if len(sys.argv) > 1 else 'npz+unit'
+    if what in ('npz', 'npz+unit'):
         main()
-    unit_scenarios()
+    if what in ('unit', 'npz+unit'):
+        unit_scenarios()
+    if what == 'all':
+        all_scenarios()
