@@ -171,6 +171,21 @@ int mpc_expand(mpc_ctx *ctx, int B, const mpc_query_desc *queries, const int32_t
                const double *parent, unsigned mode, uint32_t *out_mask, int mask_words, double *out_cost,
                int32_t *out_goal_step, mpc_stats *stats);
 
+/* -- asynchronous planning cycle --------------------------------------------------------------------------------------
+ * One planning cycle of the reference is "new prediction in, collision bits of all candidates out"
+ * (src/lowLevelPlannerManeuverAutomaton.py:19-61 per replanning step, mainCARLA.py:252-415).  mpc_submit = mpc_set_scenes
+ * (skipped with nscenes = 0: the staged scenes are kept) followed by mpc_query, WITHOUT waiting for the device: it
+ * returns as soon as copies and kernels are enqueued on the context's stream.  mpc_wait blocks until that batch is done
+ * and hands out mask and statistics exactly as mpc_query would.  Between the two calls every host buffer passed to
+ * mpc_submit must stay valid and unchanged, and no other call may be made on this context (MPC_E_STATE).  One host
+ * thread can drive several contexts of one GPU this way (submit on lane k+1 while lane k computes), which is how
+ * independent planning cycles overlap their transfers with each other's kernels without a host thread per context. */
+int mpc_submit(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_off, const double *origins,
+               const int32_t *step_obst_off, const double *obst, const int32_t *obst_nv, int Vo,
+               const int32_t *step_seg_begin, const int32_t *step_seg_end, const double *segs, int nseg,
+               int B, const mpc_query_desc *queries, const int32_t *cand_idx, int ncand, unsigned mode);
+int mpc_wait(mpc_ctx *ctx, uint32_t *out_mask, int mask_words, mpc_stats *stats);
+
 /* -- measurement helpers (bench.py) ---------------------------------------------------------------------------------
  * mpc_prepare_query stages a query batch (H2D) without running it; mpc_run_prepared launches the kernels of the
  * staged batch `iters` times on the context's stream, optionally evicting L2 (writes a buffer larger than L2)
@@ -181,6 +196,15 @@ int mpc_prepare_query(mpc_ctx *ctx, int B, const mpc_query_desc *queries, const 
                       unsigned mode);
 int mpc_run_prepared(mpc_ctx *ctx, int iters, int flush_l2, float *ms_total, float *ms_main, mpc_stats *stats);
 int mpc_fetch_mask(mpc_ctx *ctx, uint32_t *out_mask, int mask_words);
+
+/* Measured float32 arithmetic peaks of the device (the roofline denominators of bench.py; nothing of the reference
+ * corresponds to this).  Register-only instruction chains on every SM, reported in TFLOP/s (multiply-add = 2 flop,
+ * min / max = 1 flop per compared pair):
+ *   out[0] scalar FFMA        out[1] packed FFMA2 (fma.rn.f32x2)
+ *   out[2] the instruction mix of the full rectangle test as k_check runs it (8 FFMA2 : 3 FMNMX3 : 2 FMNMX, 160 flop per pair)
+ *   out[3] the same arithmetic with scalar FFMA (16 FFMA : 3 FMNMX3 : 2 FMNMX)
+ *   out[4] FMNMX3 alone   out[5] FMNMX alone   out[6] 8 FFMA : 4 FMNMX   out[7] SM clock seen (MHz, lower bound) */
+int mpc_measure_fp32_peak(mpc_ctx *ctx, double out[8]);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,13 @@ class CollisionEngine:
                     clock_khz=info.clock_khz, global_mem=info.global_mem, l2_bytes=info.l2_bytes,
                     abi_version=info.abi_version)
 
+    def measure_fp32_peak(self):
+        """measured float32 peaks of this device in TFLOP/s: scalar FFMA, packed FFMA2, the full-test instruction mix"""
+        out = (C.c_double * 8)()
+        self._check(self._L.mpc_measure_fp32_peak(self._ctx, C.byref(out)), "mpc_measure_fp32_peak")
+        return dict(ffma_tflops=out[0], ffma2_tflops=out[1], sat_mix_ffma2_tflops=out[2], sat_mix_ffma_tflops=out[3],
+                    fmnmx3_tflops=out[4], fmnmx_tflops=out[5], ffma_fmnmx_2to1_tflops=out[6], sm_mhz_seen=out[7])
+
     def pinned_like(self, array):
         """copy of `array` in page-locked host memory (mpc_alloc_pinned): host->device copies from it are real DMA"""
         a = np.ascontiguousarray(array)
@@ -183,6 +190,35 @@ class CollisionEngine:
         if rc != 0:
             self._check(rc, "mpc_query")
         return buf[:nw], (st if want_stats else None)
+
+    # -- asynchronous cycle (mpc_submit / mpc_wait) ------------------------------------------------------------------
+    def submit(self, scene_args, queries, mode=MODE_PLANNER, cand_idx=None, nw=None):
+        """stage the scenes (`scene_args` = tuple of CollisionEngine.scene_args(...), or None to keep what is staged)
+        and enqueue the query batch without waiting for the device; `wait()` returns its result.  Every array involved
+        must stay alive and unchanged until then (this object keeps references)."""
+        queries = _arr(queries, QUERY_DTYPE)
+        cand = _arr(cand_idx, np.int32) if cand_idx is not None else None
+        if nw is None:
+            nw = mask_words(queries)
+        sa = scene_args[:11] if scene_args is not None else (0, None, None, None, None, None, 4, None, None, None, 0)
+        rc = self._L.mpc_submit(self._ctx, *sa, len(queries), _cabi.ptr(queries), _cabi.ptr(cand),
+                                0 if cand is None else len(cand), int(mode))
+        if rc != 0:
+            self._check(rc, "mpc_submit")
+        if scene_args is not None:
+            self._scene_owner = None
+        self._inflight = (scene_args, queries, cand, nw)
+
+    def wait(self, want_stats=True):
+        """result of the submitted batch: (packed mask [copy], stats dict or None)"""
+        nw = self._inflight[3]
+        mask = np.empty(max(nw, 1), dtype=np.uint32)
+        st = _cabi.Stats() if want_stats else None
+        rc = self._L.mpc_wait(self._ctx, _cabi.ptr(mask), nw, C.byref(st) if want_stats else None)
+        self._inflight = None
+        if rc != 0:
+            self._check(rc, "mpc_wait")
+        return mask[:nw], (st.as_dict() if want_stats else None)
 
     def query(self, queries, cand_idx=None, mode=MODE_PLANNER):
         """returns (uint8 [sum cand_cnt] 1 = collides, stats dict)"""

@@ -50,15 +50,17 @@ def rect_vertices(cx, cy, phi, length, width):
     return np.stack([x, y], -1)
 
 
-def synthetic_library(P=4096, T=50, dt=0.1, seed=0):
-    """C4 library: P arcs of T occupancies (time offsets 0..T-1), car rectangle at every step."""
+def synthetic_library(P=4096, T=50, dt=0.1, seed=0, v_range=(0.0, 30.0), orientation_scale=1.0):
+    """C4 library: P arcs of T occupancies (time offsets 0..T-1), car rectangle at every step.  `v_range` and
+    `orientation_scale` narrow the start speeds / final headings (the mixed regime: primitives a planner would consider
+    at the ego's speed instead of the whole speed range)."""
     rng = np.random.default_rng(seed)
-    v0 = rng.uniform(0.0, 30.0, P)
+    v0 = rng.uniform(v_range[0], v_range[1], P)
     acc = rng.choice(ACCELERATIONS, P)
     tf = T * dt
     acc = np.where(v0 + acc * tf < 0.0, -v0 / tf, acc)
     acc = np.where(v0 + acc * tf > 30.0, (30.0 - v0) / tf, acc)
-    o = rng.choice(ORIENTATIONS, P)
+    o = rng.choice(ORIENTATIONS, P) * orientation_scale
     dist = v0 * tf + 0.5 * acc * tf ** 2
     steer = np.where((o == 0) | (dist <= 1e-9), 0.0, np.arctan(WHEELBASE * o / np.maximum(dist, 1e-9)))
     steer = np.clip(steer, -1.0, 1.0)
@@ -73,17 +75,22 @@ def synthetic_library(P=4096, T=50, dt=0.1, seed=0):
                 set_idx=np.arange(P, dtype=np.int32), x=x)
 
 
-def dense_traffic_scene(T=50, lanes=8, slots=32, dt=0.1, seed=1, lane_width=3.5):
-    """C4 scene: lanes x slots rectangles, constant velocity, straight multi-lane corridor as the region."""
+def dense_traffic_scene(T=50, lanes=8, slots=32, dt=0.1, seed=1, lane_width=3.5, headway=(8.0, 20.0),
+                        lane_speed=(5.0, 25.0)):
+    """C4 scene: lanes x slots rectangles, constant velocity, straight multi-lane corridor as the region.
+    Deviations from SURVEY.md 8(d), stated in bench.py's config: one cruise speed per LANE (U(lane_speed)) with +-1 m/s
+    per car instead of U(5,25) per car, and heading sigma 0.01 instead of 0.03 -- with per-car speeds the cars of a lane
+    drive through each other within the 5 s horizon."""
     rng = np.random.default_rng(seed)
     O = lanes * slots
     length = rng.uniform(3.5, 5.5, O)
     width = rng.uniform(1.6, 2.2, O)
-    head = rng.uniform(8.0, 20.0, (lanes, slots))
+    head = rng.uniform(headway[0], headway[1], (lanes, slots))
     x0 = np.cumsum(head + 5.0, axis=1).reshape(-1)
     y0 = (np.repeat(np.arange(lanes), slots) + 0.5) * lane_width + rng.normal(0.0, 0.15, O)
-    # one cruise speed per lane (U(5,25) m/s) with +-1 m/s per car, so the traffic stays a traffic for the horizon
-    v = np.repeat(rng.uniform(5.0, 25.0, lanes), slots) + rng.uniform(-1.0, 1.0, O)
+    # one cruise speed per lane with +-1 m/s per car, so the traffic stays a traffic for the horizon
+    lane_v = rng.uniform(lane_speed[0], lane_speed[1], lanes)
+    v = np.repeat(lane_v, slots) + rng.uniform(-1.0, 1.0, O)
     phi = rng.normal(0.0, 0.01, O)
     t = np.arange(T)[:, None] * dt
     cx = x0[None, :] + v[None, :] * np.cos(phi)[None, :] * t
@@ -96,7 +103,19 @@ def dense_traffic_scene(T=50, lanes=8, slots=32, dt=0.1, seed=1, lane_width=3.5)
     return dict(scene_step_off=np.array([0, T], np.int32), step_obst_off=(np.arange(T + 1) * O).astype(np.int32),
                 obst=obst, obst_nv=np.full(T * O, 4, np.int32), step_seg_begin=np.zeros(T, np.int32),
                 step_seg_end=np.full(T, 4, np.int32), segs=segs, extent=(xmin, xmax, ymin, ymax),
-                x0=x0, y0=y0, v=v, length=length, lanes=lanes, slots=slots, lane_width=lane_width)
+                x0=x0, y0=y0, v=v, length=length, lanes=lanes, slots=slots, lane_width=lane_width, lane_v=lane_v)
+
+
+def mixed_traffic_problem(P=4096, O_lanes=8, slots=32, T=50, nqueries=1, seed=0, ego_lane=3):
+    """the C4 shape (P x lanes*slots x T) in the regime a planner cares about: 30-50 % of the candidates are
+    collision-free, so they need every time step (the dense C4 scene decides 99.8 % of its candidates by collision).
+    Thinner traffic (headway U(25,60) m, lane speeds U(12,22) m/s, scene seed 101) and a library around the ego lane's
+    cruise speed (+-4 m/s, final headings x0.35, library seed = `seed`).  38 % free at the default sizes (oracle)."""
+    scene = dense_traffic_scene(T, O_lanes, slots, seed=101, headway=(25.0, 60.0), lane_speed=(12.0, 22.0))
+    v = float(scene["lane_v"][ego_lane])
+    lib = synthetic_library(P, T, seed=seed, v_range=(max(v - 4.0, 0.0), min(v + 4.0, 30.0)), orientation_scale=0.35)
+    queries, origins = dense_traffic_queries(scene, P, nqueries)
+    return lib, scene, origins, queries
 
 
 def dense_traffic_queries(scene, P, n=1, seed=2, lanes=8, lane_width=3.5):
@@ -123,6 +142,80 @@ def c4_problem(P=4096, O_lanes=8, slots=32, T=50, nqueries=1):
     scene = dense_traffic_scene(T, O_lanes, slots)
     queries, origins = dense_traffic_queries(scene, P, nqueries)
     return lib, scene, origins, queries
+
+
+def aroc_shaped_problem(P=4096, T=10, O_lanes=8, slots=32, nqueries=8, lib_verts=12, obst_verts=4, seed=7):
+    """synthetic stand-in for an AROC automaton (reference maneuverAutomaton/loadAROCautomaton.py:110-137: occupancy sets
+    are convex hulls of up to 12 vertices over time INTERVALS): P primitives x T interval occupancies, each a convex
+    `lib_verts`-gon around the swept car; every query is tested against two consecutive scenes, as the reference
+    intersects space[i] and space[i+1] for interval automata (src/lowLevelPlannerManeuverAutomaton.py:25-30).
+    obst_verts = 4: rectangle obstacles (k_check<16,4>); 8: hexagonal obstacles (k_check<16,8>).  Returns (library, scenes, origins, queries) with 2 * nqueries query records."""
+    rng = np.random.default_rng(seed)
+    dt = 0.1
+    base = synthetic_library(P, T + 1, seed=seed)
+    x = base["x"]                                                       # [P, T+1, 4]
+    mid = 0.5 * (x[:, :-1, :] + x[:, 1:, :])                            # interval centre pose
+    sweep = np.hypot(x[:, 1:, 0] - x[:, :-1, 0], x[:, 1:, 1] - x[:, :-1, 1])
+    ang = np.sort(rng.uniform(0, 2 * np.pi, (P, T, lib_verts)), axis=-1)
+    ang = ang + np.arange(lib_verts) * 1e-3                             # no coinciding vertices
+    a = (0.5 * LENGTH + 0.5 * sweep + 0.3)[..., None]                   # semi-axes: car + travelled distance + uncertainty
+    b = (0.5 * WIDTH + 0.3)
+    ex, ey = a * np.cos(ang), b * np.sin(ang)
+    c, s = np.cos(mid[..., 3])[..., None], np.sin(mid[..., 3])[..., None]
+    cx = (mid[..., 0] + B_REAR * np.cos(mid[..., 3]))[..., None]
+    cy = (mid[..., 1] + B_REAR * np.sin(mid[..., 3]))[..., None]
+    verts = np.stack([c * ex - s * ey + cx, s * ex + c * ey + cy], -1)  # [P, T, V, 2]
+    lib = dict(verts=verts, nv=np.full((P, T), lib_verts, np.int32), tidx=np.tile(np.arange(T, dtype=np.int32), (P, 1)),
+               set_off=np.array([0, P], np.int32), set_idx=np.arange(P, dtype=np.int32))
+    sc = dense_traffic_scene(T + 1, O_lanes, slots)
+    O = O_lanes * slots
+    obst = sc["obst"].reshape(T + 1, O, 4, 2)
+    if obst_verts > 4:        # hexagons: the rectangle with a 0.3 m nose and tail (six strictly convex corners)
+        r = obst[:-1]
+        u = r[:, :, 3] - r[:, :, 0]
+        u = u / np.linalg.norm(u, axis=-1, keepdims=True)
+        tail, nose = 0.5 * (r[:, :, 0] + r[:, :, 1]) - 0.3 * u, 0.5 * (r[:, :, 2] + r[:, :, 3]) + 0.3 * u
+        ob = np.zeros((T, O, 8, 2))
+        ob[:, :, :6] = np.stack([r[:, :, 0], tail, r[:, :, 1], r[:, :, 2], nose, r[:, :, 3]], axis=2)
+        nv = np.full(T * O, 6, np.int32)
+        ob = ob.reshape(T * O, 8, 2)
+    else:
+        ob, nv = obst[:-1].reshape(T * O, 4, 2), np.full(T * O, 4, np.int32)
+    # two scenes: steps 0..T-1 and the same shifted by one step (space[i] and space[i+1])
+    ob2 = (np.concatenate([ob.reshape(T, O, -1, 2)[1:], ob.reshape(T, O, -1, 2)[-1:]])).reshape(T * O, -1, 2)
+    scenes = dict(scene_step_off=np.array([0, T, 2 * T], np.int32), step_obst_off=(np.arange(2 * T + 1) * O).astype(np.int32),
+                  obst=np.concatenate([ob, ob2]), obst_nv=np.concatenate([nv, nv]),
+                  step_seg_begin=np.zeros(2 * T, np.int32), step_seg_end=np.full(2 * T, 4, np.int32), segs=sc["segs"],
+                  slots=sc["slots"], x0=sc["x0"])
+    q1, origin = dense_traffic_queries(scenes, P, nqueries)
+    q = np.concatenate([q1, q1])
+    q["scene"][nqueries:] = 1
+    return lib, scenes, np.concatenate([origin, origin]), q
+
+
+GOLDEN_SCENARIOS = None
+
+
+def load_golden_scenarios(path=None):
+    """the 100 bundled scenarios as flat arrays (tests/golden/scenarios.npz, extracted from the reference's XML files by
+    tools/make_golden.py): road boundary segments, per-step obstacle pieces, initial state, goal window"""
+    import os
+    global GOLDEN_SCENARIOS
+    if path is None:
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "scenarios.npz")
+    if GOLDEN_SCENARIOS is not None and GOLDEN_SCENARIOS[0] == path:
+        return GOLDEN_SCENARIOS[1]
+    z = np.load(path)
+    out = {}
+    for name in z["names"]:
+        m = z[name + "/meta"]
+        out[str(name)] = dict(dt=float(m[0]), t_start=int(m[1]), t_end=int(m[2]), nsteps=int(m[3]),
+                              nobstacles=int(m[4]), x0=z[name + "/x0"], goal_ring=z[name + "/goal_ring"],
+                              road=z[name + "/road"], road_safe=z[name + "/road_safe"],
+                              step_obst_off=z[name + "/step_obst_off"], obst=z[name + "/obst"],
+                              obst_nv=z[name + "/obst_nv"])
+    GOLDEN_SCENARIOS = (path, out)
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -62,16 +62,8 @@ class OracleBackend:
 
 
 def load_golden():
-    z = np.load(GOLDEN)
-    out = {}
-    for name in z['names']:
-        m = z[name + '/meta']
-        out[str(name)] = dict(dt=float(m[0]), t_start=int(m[1]), t_end=int(m[2]), nsteps=int(m[3]),
-                              nobstacles=int(m[4]), x0=z[name + '/x0'], goal_ring=z[name + '/goal_ring'],
-                              road=z[name + '/road'], road_safe=z[name + '/road_safe'],
-                              step_obst_off=z[name + '/step_obst_off'], obst=z[name + '/obst'],
-                              obst_nv=z[name + '/obst_nv'])
-    return out
+    from motionplanner_b200.workloads import load_golden_scenarios
+    return load_golden_scenarios(GOLDEN)
 
 
 def scenario_scene(g, region='road_safe'):

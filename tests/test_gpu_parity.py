@@ -557,7 +557,7 @@ def test_scout_launch_regime(eng, monkeypatch):
     pb = orc.Problem(lib, sc)
     want, ost = pb.check(q, None, orc.MODE_NO_EARLY_EXIT)
     got, st = eng.query(q, None, MODE_PLANNER)
-    assert st["kernels"] == 3                                  # scout + main + refine: the heuristic picked the regime
+    assert st["kernels"] == 4                                  # clear + scout + main + refine: the heuristic picked the regime
     assert np.array_equal(got, want) and st["pairs_nominal"] == ost["pairs_nominal"]
     wantv, _ = pb.check(q, None, orc.MODE_STRICT | orc.MODE_NO_EARLY_EXIT)
     gotv, _ = eng.query(q, None, MODE_VALIDATOR)
@@ -569,7 +569,7 @@ def test_scout_launch_regime(eng, monkeypatch):
         else:
             monkeypatch.setenv("MPC_SCOUT_GPC", str(sgpc))
         got2, st2 = eng.query(q, None, MODE_PLANNER)
-        assert st2["kernels"] == 2 + scouts
+        assert st2["kernels"] == 3 + scouts
         assert np.array_equal(got2, want) and st2["pairs_nominal"] == ost["pairs_nominal"], (scouts, sgpc)
     # small problems with forced scouts (multi-phase tiles, general polygons, explicit lists)
     monkeypatch.setenv("MPC_SCOUTS", "2")

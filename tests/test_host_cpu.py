@@ -177,7 +177,7 @@ def test_scene_args_marshalling_without_a_device():
     assert len(args) == 12 and args[0] == 1 and args[6] == sc["obst"].shape[1] and args[10] == len(sc["segs"])
     keep = args[11]
     assert keep[3].dtype == np.float64 and keep[3].flags.c_contiguous and keep[4].dtype == np.int32
-    assert args[4].value == keep[3].ctypes.data                     # pointer to the kept obstacle array
+    assert args[4] == keep[3].ctypes.data                           # address of the kept obstacle array
     bad = dict(scene, obst_nv=sc["obst_nv"][:-1])
     with pytest.raises(AssertionError):
         CollisionEngine.scene_args(*[bad[k] for k in keys])
