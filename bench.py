@@ -536,18 +536,20 @@ def main():
     lane_q = [pool.pinned_like(poses[0]) for _ in range(lanes)]
     ncycles = args.steps * K
 
+    pose_bytes = [x.view(np.uint8) for x in poses]
+
     def refill(i, sc, q):
         np.copyto(sc["obst"], variants[i % NPOSE])        # the new prediction of this cycle (819 KB memcpy, counted)
-        np.copyto(q, poses[(i // NPOSE) % NPOSE])
+        np.copyto(q.view(np.uint8), pose_bytes[(i // NPOSE) % NPOSE])      # (a record-wise copy of the 4 KB costs 10 us)
 
     def cycles_for(n):
         return [(lane_scene[i % lanes], lane_q[i % lanes]) for i in range(n)]
 
     mode_e2e = MODE_PLANNER | MODE_NO_TIMING
-    pool.run_cycles(cycles_for(args.warmup * lanes * 2), mode_e2e, refill=refill)
+    pool.run_cycles(cycles_for(args.warmup * lanes * 2), mode_e2e, refill=refill, want_stats=False)
     barrier()
     t0 = time.perf_counter()
-    res = pool.run_cycles(cycles_for(ncycles), mode_e2e, refill=refill)
+    res = pool.run_cycles(cycles_for(ncycles), mode_e2e, refill=refill, want_stats=False)
     barrier()
     e2e_s = time.perf_counter() - t0
     # check the last cycles against a synchronous single-context run of the same inputs
@@ -562,10 +564,10 @@ def main():
     for lsc, lq in zip(lane_scene, lane_q):
         np.copyto(lsc["obst"], variants[0])
         np.copyto(lq, poses[0])
-    pool.run_cycles(cycles_for(lanes * 2), mode_e2e, marshal_once=True)
+    pool.run_cycles(cycles_for(lanes * 2), mode_e2e, marshal_once=True, want_stats=False)
     barrier()
     t0 = time.perf_counter()
-    pool.run_cycles(cycles_for(ncycles), mode_e2e, marshal_once=True)
+    pool.run_cycles(cycles_for(ncycles), mode_e2e, marshal_once=True, want_stats=False)
     barrier()
     e2e_cached_s = time.perf_counter() - t0
     pool.close()
@@ -723,8 +725,12 @@ def main():
             "wall_s_timed_region": wall, "device": info["name"], "sm_count": info["sm_count"],
         }
         if extras:
-            line["latency"] = latency_block(lambda: CollisionEngine(local))
-            line["aroc_shaped"] = aroc_block(eng, peak_tflops)
+            for key, fn in (("latency", lambda: latency_block(lambda: CollisionEngine(local))),
+                            ("aroc_shaped", lambda: aroc_block(eng, peak_tflops))):
+                try:
+                    line[key] = fn()
+                except Exception as exc:          # noqa: BLE001 -- a side block must not cost the headline line
+                    line[key] = {"error": "%s: %s" % (type(exc).__name__, exc)}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as orc
             orc.build()

@@ -96,4 +96,4 @@ def load():
 def ptr(a):
     """address of a numpy array's data for a c_void_p argument (None for empty / missing).  A plain int: going through
     `a.ctypes.data_as` costs ~4 us per array, eight arrays per mpc_set_scenes"""
-    return a.__array_interface__['data'][0] if a is not None and a.size else None
+    return a.ctypes.data if a is not None and a.size else None

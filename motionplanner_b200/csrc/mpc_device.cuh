@@ -55,8 +55,11 @@ struct KParams {
     int sg_stride;
     const float *maxabs_scene;
     // queries
-    int c_total;                 // CTAs per time slot: the grid is c_total * J blocks, slot-major
+    int c_total;                 // CTAs per time slot: the grid is (c_total, level groups), slot-major
+    int wsplit;                  // k_check<..., WS = true>: warps per candidate group (2, 4 or 8)
+    int levels;                  // time slots one CTA walks through in sequence (1: one slot per CTA; scout launches: several)
     int compact;                 // renumber the undecided candidates densely (needs: every library slot occupied, big CTAs)
+    int cmin;                    // ... in CTAs of at least this many groups (the pre-pass has to pay for itself)
     int cross_exit;              // grid larger than one resident wave: later time slots may use the bits of earlier ones
     const QDev *q;
     const int2 *cta_tab;         // [c_total] (query, chunk) of every CTA of one time slot, built by the host with the batch
@@ -529,36 +532,10 @@ __device__ __forceinline__ float min_dist(const PolyRegs<VQ> &Q, float nx, float
     return mn;
 }
 
-// the same with scalar FFMA.  Measured on B200 (mpc_measure_fp32_peak): FFMA issues every 1.05 clk per scheduler,
-// FFMA2 every 2.18 clk, FMNMX / FMNMX3 every 2 clk, and the pipes do not overlap -- so a packed multiply-add saves an
-// issue slot but no pipe time.  Where the arithmetic pipe is the limit (k_check_full) the scalar form is ~15 % faster
-// (60.1 vs 52.4 TFLOP/s for the instruction mix of the rectangle test); where issue slots are (k_check) packed wins.
-template <int VQ>
-__device__ __forceinline__ float min_dist_scalar(const PolyRegs<VQ> &Q, float nx, float ny, float c) {
-    float mn = BIG;
-#pragma unroll
-    for (int h = 0; h < VQ / 2; h++) {
-        const float d0 = fmaf(nx, lo32(Q.X[h]), fmaf(ny, lo32(Q.Y[h]), -c));
-        const float d1 = fmaf(nx, hi32(Q.X[h]), fmaf(ny, hi32(Q.Y[h]), -c));
-        mn = (h == 0) ? fminf(d0, d1) : min3(mn, d0, d1);
-    }
-    return mn;
-}
-
-template <int VA, int VB>
-__device__ __forceinline__ float sat_polys_scalar(const PolyRegs<VA> &A, const PolyRegs<VB> &B) {
-    float sep = -BIG;
-#pragma unroll
-    for (int e = 0; e < VA; e += 2)
-        sep = max3(sep, min_dist_scalar<VB>(B, A.ln[3 * e], A.ln[3 * e + 1], A.ln[3 * e + 2]),
-                   min_dist_scalar<VB>(B, A.ln[3 * e + 3], A.ln[3 * e + 4], A.ln[3 * e + 5]));
-#pragma unroll
-    for (int e = 0; e < VB; e += 2)
-        sep = max3(sep, min_dist_scalar<VA>(A, B.ln[3 * e], B.ln[3 * e + 1], B.ln[3 * e + 2]),
-                   min_dist_scalar<VA>(A, B.ln[3 * e + 3], B.ln[3 * e + 4], B.ln[3 * e + 5]));
-    return sep;
-}
-
+// (A scalar-FFMA form of the same test was measured in k_check_full: the register-only instruction mix runs 15 % faster
+// with scalar FFMA -- 60.1 vs 52.4 TFLOP/s, mpc_measure_fp32_peak -- because FFMA2 issues every 2.18 clk against 1.05 clk
+// for FFMA while min / max take 2 clk and do not overlap with either; inside the kernel the extra 32 issue slots per
+// test cost more than that: 2.42e11 checks/s scalar vs 2.73e11 packed.)
 // signed separation of two convex polygons: max over all edge axes of the minimum vertex distance (> 0 apart)
 template <int VA, int VB>
 __device__ __forceinline__ float sat_polys(const PolyRegs<VA> &A, const PolyRegs<VB> &B) {
@@ -601,7 +578,11 @@ constexpr int QCAP = 64;            // per-warp queue of (lane, record) pairs th
 // The kernel is sensitive to its shape: with that code present C4 (4 segments per step) runs 5 % slower; the same
 // switch for obstacles changes nothing, and funnelling the three inlined copies of each drain into one call site
 // (smaller code, more control flow per round) costs 8-15 %.
-template <int VA, int VB, bool COUNT, bool SEGCULL>
+// WS: "warps over obstacles".  A CTA with fewer candidate groups than warps (planner-sized queries: one to four groups
+// per CTA) gives every group to WO = p.wsplit warps; each takes every WO-th block of 32 obstacle slots / boundary
+// segments of the tile and the partial results (collision bits, crossing parity) are merged in shared memory.  Without it
+// seven of the eight warps of such a CTA idle while one walks the whole tile (2362 segments on the ZAM_ACC map).
+template <int VA, int VB, bool COUNT, bool SEGCULL, bool WS>
 __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p) {
     constexpr int F = ob_fields(VB), FA = ob_fields(VA), NW = K_THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -609,7 +590,8 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
     unsigned *s_coll = reinterpret_cast<unsigned *>(smem_raw + 16);
     unsigned *s_par = s_coll + GPC_MAX;
     unsigned *s_punc = s_par + GPC_MAX;
-    unsigned *s_q = s_punc + GPC_MAX;                                          // [NW][QCAP]
+    unsigned *s_donew = s_punc + GPC_MAX;                                      // collision words of the CTA's groups so far
+    unsigned *s_q = s_donew + GPC_MAX;                                         // [NW][QCAP]
     float4 *s_A = reinterpret_cast<float4 *>(s_q + NW * QCAP);                 // [NW][FA][32] occupancy polygons
     float4 *s_ob = s_A + NW * FA * 32;                                         // [F][cap_o] obstacle records
     float *s_c = reinterpret_cast<float *>(s_ob + F * p.cap_o);                // circle x | y | -(r + rcull)^2
@@ -617,51 +599,31 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
+    const int WO = WS ? p.wsplit : 1;                 // warps per group
+    const int wg = WS ? warp / WO : warp, wo = WS ? warp - wg * WO : 0, GW = WS ? NW / WO : NW;
+    unsigned *s_act = s_donew;                        // WS: candidates of the group that hold an occupancy (no done words there)
     pdl_trigger();                    // the next kernel of the step (main launch / k_refine) may start its own prologue
 
-    // which (slot, query, chunk) is this CTA.  The grid is SLOT-major: all queries' CTAs of time slot 0 come first, then
-    // slot 1, ...  CTAs start in index order, so by the time the later slots of a batch run, the earlier ones have
-    // published their collision bits and whole groups can return early (see `done` below).  (query, chunk) of the CTA
-    // within its slot come from a table the host packs with the batch (one load instead of a search over the queries).
-    const int c_total = p.c_total;                              // CTAs per time slot (sum of the queries' chunks)
-    const int level = (int)blockIdx.x / c_total, cidx = (int)blockIdx.x - level * c_total;
-    const int j = __ldg(p.slot_perm + level);
-    const int2 ent = __ldg(p.cta_tab + cidx);
+    // which (slots, query, chunk) is this CTA.  The grid is SLOT-major: blockIdx.y counts groups of `levels` consecutive
+    // entries of the slot order, blockIdx.x the (query, chunk) pairs of the batch; CTAs start in index order, so by the
+    // time the later slots of a batch run, the earlier ones have published their collision bits and whole groups can
+    // return early (see `done` below).  (query, chunk) come from a table the host packs with the batch.
+    const int2 ent = __ldg(p.cta_tab + blockIdx.x);
     const int q = ent.x;
     const QDev *Q = p.q + q;
     const int chunk = ent.y;
-    int t = Q->t0 + p.slot_t[j];
-    // reference guards: ind + time <= param['steps'] and ind + time < len(space)  (lowLevelPlannerManeuverAutomaton.py:120,122)
-    if (blockIdx.x == 0 && tid == 0) {     // for the statistics: the host never reads the scene's extent itself
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {     // for the statistics: the host never reads the scene's extent itself
         pdl_wait();                        // (the result block is cleared by the kernel before this one)
         p.cnt->tau = fmaxf(fmaxf(*p.maxabs_scene, *p.maxabs_query) * (1.0f / 131072.0f), 1e-7f);
     }
-    if (t > Q->step_limit || t < 0 || t >= Q->nsteps) return;
-    int step = Q->step0 + t;
-    // obstacles of the step: a 32-aligned slot range (padding slots are far away), `nobst` real ones
-    const int o0 = p.step_obst_off[step], nslot = p.step_obst_off[step + 1] - o0, nobst = p.step_obst_cnt[step];
-    const int g0 = p.step_seg_begin[step];
-    const bool has_region = g0 >= 0;
-    const int nseg = has_region ? p.step_seg_end[step] - g0 : 0;
     const int cand_cnt = Q->cand_cnt, cand_base = Q->cand_base;
     const int gbeg = chunk * p.gpc;
     const int ng = min(p.gpc, (cand_cnt + 31) / 32 - gbeg);
     const float lx = Q->lx, ly = Q->ly, lc = Q->lc, ls = Q->ls;
+    const int q_t0 = Q->t0, q_limit = Q->step_limit, q_nsteps = Q->nsteps, q_step0 = Q->step0;
     // float32 error band: every float32 signed distance below is within tau of its float64 value
     const float tau = fmaxf(fmaxf(*p.maxabs_scene, *p.maxabs_query) * (1.0f / 131072.0f), 1e-7f);
     const bool noexit = p.mode & MPC_MODE_NO_EARLY_EXIT;
-
-    if (tid == 0) mbar_init(bar, 1);
-    for (int i = tid; i < 3 * GPC_MAX; i += K_THREADS) s_coll[i] = 0;
-    __syncthreads();
-    // Everything above reads what the host staged before the step.  What follows reads the result words earlier launches
-    // of the step publish (early return across time slots) or adds to the result block: a launch that looks at those
-    // words waits for its predecessor here, one that does not waits only when its first tile has landed.
-    const bool xexit = p.cross_exit && !noexit;
-    if (xexit) pdl_wait();
-
-    const int nph_o = (nslot + p.cap_o - 1) / p.cap_o, nph_s = (nseg + p.cap_s - 1) / p.cap_s;
-    const int nphase = max(1, max(nph_o, nph_s));
     // cull radius shared by the whole CTA: largest library bounding radius + band (conservative for smaller polygons)
     const float rcull = p.lib_rmax + 2.0f * tau;
     unsigned n_cull = 0, n_axis = 0, n_skip = 0, n_done = 0;
@@ -669,19 +631,53 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
     const int pos_base = Q->pos_base;
     float4 *sA = s_A + warp * FA * 32;
     unsigned *sq = s_q + warp * QCAP;
+    unsigned nom = 0;                             // nominal pairs of this warp's groups (one atomic at the end)
+    unsigned *s_live = s_par, *s_pref = s_punc, *s_gstart = s_coll;       // s_gstart[g]: word holding rank 32 g
+    unsigned *s_tot = reinterpret_cast<unsigned *>(smem_raw + 8);          // (the mbarrier uses bytes 0..7)
+
+    if (tid == 0) mbar_init(bar, 1);
+    for (int i = tid; i < GPC_MAX; i += K_THREADS) s_donew[i] = 0;
+    unsigned tile_no = 0;             // tiles fetched so far (CTA-uniform): parity of the mbarrier phase to wait for
+    bool waited = false;              // pdl_wait() done (CTA-uniform)
+    bool loaded = false;              // s_donew holds the words earlier launches published (CTA-uniform)
+
+    // One time slot.  A CTA of a multi-level launch runs this for `levels` consecutive entries of the slot order and keeps
+    // the collision words of its candidates in shared memory in between: what an earlier slot decided is skipped at the
+    // later ones at once, without the round trip through the result words in L2 that separate CTAs need (and without the
+    // first-wave blindness of a slot-major grid: the CTAs of one wave cannot see each other's bits).
+    auto run_level = [&](const int lv) {
+    const int j = __ldg(p.slot_perm + blockIdx.y * p.levels + lv);
+    const int t = q_t0 + __ldg(p.slot_t + j);
+    if (lv > 0) __syncthreads();      // every warp is done with the previous slot: its tile, its group state, its s_donew updates
+    for (int i = tid; i < 3 * GPC_MAX; i += K_THREADS) s_coll[i] = 0;
+    __syncthreads();
+    // reference guards: ind + time <= param['steps'] and ind + time < len(space)  (lowLevelPlannerManeuverAutomaton.py:120,122)
+    if (t > q_limit || t < 0 || t >= q_nsteps) return;
+    const int step = q_step0 + t;
+    // obstacles of the step: a 32-aligned slot range (padding slots are far away), `nobst` real ones
+    const int o0 = p.step_obst_off[step], nslot = p.step_obst_off[step + 1] - o0, nobst = p.step_obst_cnt[step];
+    const int g0 = p.step_seg_begin[step];
+    const bool has_region = g0 >= 0;
+    const int nseg = has_region ? p.step_seg_end[step] - g0 : 0;
+    // Everything above reads what the host staged before the step.  What follows reads the result words earlier launches
+    // of the step publish (early return across time slots) or adds to the result block: a launch that looks at those
+    // words waits for its predecessor here, one that does not waits only when its first tile has landed.
+    const bool xexit = (p.cross_exit || lv > 0) && !noexit;
+    const bool from_global = p.cross_exit && !loaded;      // first look: the words in L2, afterwards the CTA's own copy
+    if (xexit && !waited) { pdl_wait(); waited = true; }
+
+    const int nphase = (nslot <= p.cap_o && nseg <= p.cap_s) ? 1 : max((nslot + p.cap_o - 1) / p.cap_o, (nseg + p.cap_s - 1) / p.cap_s);
 
     // ---- early return of the whole CTA, before any tile is fetched.  In a batch big enough that later time slots start
     // after earlier ones have finished, the result words already hold the collision bits of those slots: if none of the
     // CTA's candidates is still undecided there is nothing left to do -- the reference returns at the first violation
     // too (collision_check :124, collisionChecker.py:22,33).  Only the nominal pair statistic is kept exact.
-    unsigned nom = 0;                             // nominal pairs of this warp's groups (one atomic at the end)
     // Compaction: when every library slot is occupied (so "candidate" = "occupancy present") and the step fits one tile,
     // the undecided candidates of the CTA are renumbered densely -- groups are formed from the live ones only, instead
     // of running every group that still has one straggler.  s_par / s_punc (multi-phase state, unused here) hold the
-    // live words and their running counts.
-    const bool cmode = xexit && p.compact && nphase == 1 && ng >= 32;      // the pre-pass pays from ~32 groups on
-    unsigned *s_live = s_par, *s_pref = s_punc, *s_gstart = s_coll;       // s_gstart[g]: word holding rank 32 g
-    unsigned *s_tot = reinterpret_cast<unsigned *>(smem_raw + 8);          // (the mbarrier uses bytes 0..7)
+    // live words and their running counts.  The pre-pass pays from ~32 groups on for a CTA that has to fetch its words
+    // from L2; at the later slots of a multi-level CTA they sit in shared memory and most groups are stragglers.
+    const bool cmode = !WS && xexit && p.compact && nphase == 1 && ng >= (lv > 0 ? 4 : p.cmin);
     int total_live = 0;
     if (cmode) {
         if (warp == 0) {
@@ -693,7 +689,9 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
                 if (i < ng) {
                     const int nvalid = min(32, cand_cnt - (gbeg + i) * 32);
                     const unsigned valid = nvalid >= 32 ? FULL : ((1u << nvalid) - 1u);
-                    live = valid & ~__ldcg(maskp + gbeg + i);
+                    unsigned dw = s_donew[i];
+                    if (from_global) { dw |= __ldcg(maskp + gbeg + i); s_donew[i] = dw; }
+                    live = valid & ~dw;
                     s_live[i] = live;
                 }
                 cnt[r] = run;
@@ -720,6 +718,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
             if (lane == 31) *s_tot = incl;
         }
         __syncthreads();
+        if (from_global) loaded = true;
         total_live = (int)*s_tot;
         if (tid == 0) {                              // the statistic needs no library access here
             const unsigned long long w = (unsigned long long)min(ng * 32, cand_cnt - gbeg * 32) * (unsigned)(nobst + nseg);
@@ -731,22 +730,27 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
         bool live = false;
         for (int g = warp; g < ng; g += NW) {
             const int ci = (gbeg + g) * 32 + lane;
-            if (ci < cand_cnt && !((__ldcg(maskp + gbeg + g) >> lane) & 1u)) live = true;
+            unsigned dw = s_donew[g];
+            if (from_global) {
+                dw |= __ldcg(maskp + gbeg + g);
+                __syncwarp();
+                if (lane == 0) s_donew[g] = dw;
+            }
+            if (ci < cand_cnt && !((dw >> lane) & 1u)) live = true;
         }
+        if (from_global) loaded = true;
         if (!__syncthreads_or(live)) {
+            unsigned skipped = 0;
             for (int g = warp; g < ng; g += NW) {
                 const int ci = (gbeg + g) * 32 + lane;
                 if (ci < cand_cnt) {
                     const size_t pj = pos_base >= 0 ? (size_t)j * p.set_total + pos_base + ci
                                                     : (size_t)__ldg(p.cand + cand_base + ci) * p.J + j;
-                    if (__ldg((pos_base >= 0 ? p.slib_c : p.lib_c) + pj).w > 0.f) nom += (unsigned)(nobst + nseg);
+                    if (__ldg((pos_base >= 0 ? p.slib_c : p.lib_c) + pj).w > 0.f) skipped += (unsigned)(nobst + nseg);
                 }
             }
-            nom = __reduce_add_sync(FULL, nom);
-            if (lane == 0 && nom) {
-                atomicAdd(&p.cnt->pairs_nominal, (unsigned long long)nom);
-                if (COUNT) atomicAdd(&p.cnt->done_skipped, (unsigned long long)nom);
-            }
+            nom += skipped;
+            if (COUNT) n_done += skipped;
             return;
         }
     }
@@ -769,7 +773,8 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
                     tma_bulk_g2s(s_sg + f * p.cap_s, p.sg_f + (size_t)f * p.sg_stride + g0 + sc0, scn * 16, bar);
         }
         if (loading) {
-            mbar_wait(bar, ph & 1);
+            mbar_wait(bar, tile_no & 1);
+            tile_no++;
             // third circle array: r  ->  -(r + rcull)^2, the constant term of the centre-line test
             for (int i = tid; i < ocn; i += K_THREADS) {
                 float r = s_c[2 * p.cap_o + i] + rcull;
@@ -777,15 +782,15 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
             }
             __syncthreads();
         }
-        if (!xexit && ph == 0) pdl_wait();
+        if (!waited) { pdl_wait(); waited = true; }
         // candidate index of the warp's first group; the next group's is fetched
         // while the current one is processed, which takes one link out of the dependent-load chain of the set-up
         int nxt_prim = 0;
         {
-            const int ci0 = (gbeg + warp) * 32 + lane;
-            if (!cmode && pos_base < 0 && warp < ng && ci0 < cand_cnt) nxt_prim = __ldg(p.cand + cand_base + ci0);
+            const int ci0 = (gbeg + wg) * 32 + lane;
+            if (!cmode && pos_base < 0 && wg < ng && ci0 < cand_cnt) nxt_prim = __ldg(p.cand + cand_base + ci0);
         }
-        for (int g = warp; g < ngl; g += NW) {
+        for (int g = wg; g < ngl; g += GW) {
             // ---- lane = one candidate primitive: transform its occupancy polygon, park it in shared memory ----------
             int ci = (gbeg + g) * 32 + lane;
             bool active = ci < cand_cnt;
@@ -810,8 +815,8 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
             if (cmode && !direct && active) nxt_prim = __ldg(p.cand + cand_base + ci);
             if (active) pj = direct ? (size_t)j * p.set_total + pos_base + ci : (size_t)nxt_prim * p.J + j;
             if (!direct && !cmode) {
-                const int cin = ci + NW * 32;
-                if (g + NW < ng && cin < cand_cnt) nxt_prim = __ldg(p.cand + cand_base + cin);
+                const int cin = ci + GW * 32;
+                if (g + GW < ng && cin < cand_cnt) nxt_prim = __ldg(p.cand + cand_base + cin);
             }
             float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
             if (active) cc = __ldg((direct ? p.slib_c : p.lib_c) + pj);
@@ -821,7 +826,8 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
                 // the same test per group: collision bits other time slots have published (L2, not L1).
                 // Every candidate of the group collides at another time step already: the reference returns at the
                 // first violation too (collision_check :124, collisionChecker.py:22,33).
-                done = __ldcg(maskp + gbeg + g);
+                done = s_donew[g];
+                if (p.cross_exit) done |= __ldcg(maskp + gbeg + g);      // what other CTAs have published meanwhile
                 if (__all_sync(FULL, !active || ((done >> lane) & 1u))) {
                     if (active && ph == 0) {
                         nom += (unsigned)(nobst + nseg);
@@ -830,7 +836,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
                     continue;
                 }
             }
-            if (!cmode && active && ph == 0) nom += (unsigned)(nobst + nseg);
+            if (!cmode && active && ph == 0 && wo == 0) nom += (unsigned)(nobst + nseg);
             {
                 float ax[VA], ay[VA], ln[((VA * 3 + 3) / 4) * 4];
 #pragma unroll
@@ -966,7 +972,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
                     }
                     live_o = (unsigned long long)__ballot_sync(FULL, l0) | ((unsigned long long)__ballot_sync(FULL, l1) << 32);
                 }
-                for (int ob = 0; ob < ocn; ob += 32) {
+                for (int ob = wo * 32; ob < ocn; ob += 32 * WO) {
                     const unsigned m4 = (unsigned)(live_o >> (ob >> 3)) & 0xFu;
                     if (COUNT && active) {
 #pragma unroll
@@ -1067,7 +1073,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
                     bool near = (fabsf(dl) <= arr) & (fabsf(tt) <= sl.w + arr);
                     if (near) hits |= 0x80000000u >> k;
                 };
-                for (int sb = 0; sb < scn; sb += 32) {
+                for (int sb = wo * 32; sb < scn; sb += 32 * WO) {
                     const int cnt = min(32, scn - sb);
                     unsigned hits = 0;
                     if (!blockcull) {
@@ -1099,6 +1105,17 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
 
             // ---- fold this phase into the group state ----------------------------------------------------------
             unsigned bc = __ballot_sync(FULL, collide), bp = __ballot_sync(FULL, par), bu = __ballot_sync(FULL, punc);
+            if (WS) {
+                // several warps share the group: merge the partial results; published after the last phase (below)
+                if (lane == 0) {
+                    if (bc) atomicOr(s_coll + g, bc);
+                    if (bp) atomicXor(s_par + g, bp);
+                    if (bu) atomicOr(s_punc + g, bu);
+                }
+                const unsigned ba = __ballot_sync(FULL, active);
+                if (lane == 0 && wo == 0 && ph == 0) s_act[g] = ba;
+                continue;
+            }
             if (nphase > 1) {
                 if (lane == 0) { s_coll[g] |= bc; s_par[g] ^= bp; s_punc[g] |= bu; }
                 __syncwarp();
@@ -1113,15 +1130,40 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
                 // spatially sorted candidate sets: bits in sorted order, k_refine moves them home
                 unsigned *out = (pos_base < 0 ? p.mask : p.mask_sorted) + Q->mask_off;
                 if (cmode) {    // compacted group: every lane has its own word
-                    if (coll && active) atomicOr(out + (ci >> 5), 1u << (ci & 31));
+                    if (coll && active) {
+                        atomicOr(out + (ci >> 5), 1u << (ci & 31));
+                        if (p.levels > 1) atomicOr(s_donew + ((ci >> 5) - gbeg), 1u << (ci & 31));
+                    }
                 } else {
                     unsigned word = __ballot_sync(FULL, coll && active);
-                    if (lane == 0 && word) atomicOr(out + gbeg + g, word);
+                    if (lane == 0 && word) {
+                        atomicOr(out + gbeg + g, word);
+                        if (p.levels > 1) s_donew[g] |= word;
+                    }
                 }
             }
         }
-        if (nphase > 1) __syncthreads();      // everyone is done with the tile before the next bulk copy overwrites it
+        if (nphase > 1 || WS) __syncthreads();      // everyone is done with the tile before the next bulk copy overwrites it
     }
+    if (WS) {
+        // the merged state of every group (the barrier above closed the last phase): one warp per group publishes
+        unsigned *out = (pos_base < 0 ? p.mask : p.mask_sorted) + Q->mask_off;
+        for (int g = warp; g < ng; g += NW) {
+            const unsigned bc = s_coll[g], bp = s_par[g], bu = s_punc[g], ba = s_act[g];
+            const int ci = (gbeg + g) * 32 + lane;
+            const bool active = (ba >> lane) & 1u;
+            bool coll = (bc >> lane) & 1u;
+            if (has_region && active && !coll) {
+                if ((bu >> lane) & 1u) push_work(p, q, ci, j, KIND_PARITY, 0);
+                else if (!((bp >> lane) & 1u)) coll = true;        // centre outside the region
+            }
+            const unsigned word = __ballot_sync(FULL, coll && active);
+            if (lane == 0 && word) atomicOr(out + gbeg + g, word);
+        }
+    }
+    };      // run_level
+
+    for (int lv = 0; lv < p.levels; lv++) run_level(lv);
     nom = __reduce_add_sync(FULL, nom);
     if (lane == 0 && nom) atomicAdd(&p.cnt->pairs_nominal, (unsigned long long)nom);
     if (COUNT) {
@@ -1156,19 +1198,17 @@ __global__ void __launch_bounds__(K_THREADS, 2) k_check_full(const KParams p) {
     unsigned *s_coll = reinterpret_cast<unsigned *>(smem_raw + 16);            // same carve-up as k_check (one size)
     unsigned *s_par = s_coll + GPC_MAX;
     unsigned *s_punc = s_par + GPC_MAX;
-    float4 *s_ob = reinterpret_cast<float4 *>(s_punc + GPC_MAX + NW * QCAP) + NW * FA * 32;
+    float4 *s_ob = reinterpret_cast<float4 *>(s_punc + 2 * GPC_MAX + NW * QCAP) + NW * FA * 32;
     float4 *s_sg = reinterpret_cast<float4 *>(reinterpret_cast<float *>(s_ob + F * p.cap_o) + 3 * p.cap_o);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();
-    const int c_total = p.c_total;
-    const int level = (int)blockIdx.x / c_total, cidx = (int)blockIdx.x - level * c_total;
-    const int j = __ldg(p.slot_perm + level);
-    const int2 ent = __ldg(p.cta_tab + cidx);
+    const int j = __ldg(p.slot_perm + blockIdx.y);               // grid: (CTAs of one time slot, time slots), slot-major
+    const int2 ent = __ldg(p.cta_tab + blockIdx.x);
     const int q = ent.x, chunk = ent.y;
     const QDev *Q = p.q + q;
     const int t = Q->t0 + p.slot_t[j];
     const float tau = fmaxf(fmaxf(*p.maxabs_scene, *p.maxabs_query) * (1.0f / 131072.0f), 1e-7f);
-    if (blockIdx.x == 0 && tid == 0) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
         pdl_wait();
         p.cnt->tau = tau;
     }
@@ -1257,7 +1297,7 @@ __global__ void __launch_bounds__(K_THREADS, 2) k_check_full(const KParams p) {
                 B.load(s_ob, p.cap_o, k);
 #pragma unroll
                 for (int u = 0; u < NP; u++) {
-                    const float sep = sat_polys_scalar<VA, VB>(A[u], B);
+                    const float sep = sat_polys<VA, VB>(A[u], B);
                     if (active[u]) {
                         if (COUNT) n_axis++;
                         if (sep < -tau) collide[u] = true;

@@ -89,7 +89,8 @@ struct mpc_ctx {
     void *res_p = nullptr;        // result block of the prepared batch: inside qpack_d (fused_clear) or res_d
     bool fused_clear = false;     // small result blocks are cleared by the zeros the query upload carries
     size_t qpack_cta_off = 0, qpack_cta2_off = 0, qpack_hdr_off = 0, up_bytes = 0, up_cand_bytes = 0, up_cand_src = 0;
-    int scouts = 0, scout_gpc = 1, scout_c_total = 0;      // leading time slots launched on their own (see launch_check)
+    int wsplit = 1;               // warps per candidate group in k_check (few groups per CTA)
+    int scouts = 0, scout_gpc = 1, scout_c_total = 0, scout_levels = 1;      // leading time slots launched on their own (see launch_check)
     unsigned long long generation = 0;          // bumped whenever a pointer a captured graph holds may have changed
     std::map<std::vector<long long>, cudaGraphExec_t> graphs;
     std::map<std::vector<long long>, cudaGraphExec_t> scene_graphs;      // staging of small scenes from pinned arrays
@@ -830,9 +831,13 @@ static KParams make_params(mpc_ctx *ctx) {
     // early return across time slots needs earlier slots to have finished: only grids beyond one resident wave
     // compaction of the undecided candidates costs a serial pre-pass per CTA: it pays from ~32 groups per CTA on
     // (C4, ms per batch of 4 / 8 / 16 / 64 queries: 0.073 / 0.085 / 0.111 / 0.219 with, 0.066 / 0.088 / 0.123 / 0.307 without)
-    p.compact = (ctx->lib_full && ctx->gpc >= 32) ? 1 : 0;
+    p.compact = (ctx->lib_full && (ctx->gpc >= 32 || ctx->scout_levels > 1)) ? 1 : 0;
     if (getenv("MPC_NO_COMPACT")) p.compact = 0;                                                // tuning hook
+    p.cmin = 32;
+    if (const char *e = getenv("MPC_CMODE_MIN")) { p.cmin = std::max(1, atoi(e)); if (ctx->lib_full) p.compact = 1; }      // tuning hook
     p.c_total = ctx->J > 0 ? ctx->ctas / ctx->J : 0;
+    p.levels = 1;
+    p.wsplit = ctx->wsplit;
     p.cross_exit = ctx->ctas > ctx->prop.multiProcessorCount * K_MIN_CTAS;
     p.q = (const QDev *)qp; p.cta_tab = (const int2 *)(qp + ctx->qpack_cta_off); p.cand = (const int *)ctx->cand_d.p;
     p.cand_pos = (const int *)ctx->sets_pos.p;
@@ -853,10 +858,9 @@ static KParams make_params(mpc_ctx *ctx) {
 static const bool g_use_pdl = getenv("MPC_NO_PDL") == nullptr;
 
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool dependent, Args... args) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, int block, size_t smem, cudaStream_t st, bool dependent, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -866,22 +870,24 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
 }
 
 template <int VA, int VB, bool SEGCULL>
-static cudaError_t launch_check_vb(mpc_ctx *ctx, const KParams &p, int grid, bool dependent) {
+static cudaError_t launch_check_vb(mpc_ctx *ctx, const KParams &p, dim3 grid, bool dependent) {
     const bool count = ctx->mode & MPC_MODE_COUNT_WORK;
     if (ctx->mode & MPC_MODE_NO_CULL)          // full evaluation: its own kernel, two occupancy polygons per lane
         return launch_pdl(count ? k_check_full<VA, VB, true> : k_check_full<VA, VB, false>, grid, K_THREADS, ctx->smem, ctx->stream, dependent, p);
-    return launch_pdl(count ? k_check<VA, VB, true, SEGCULL> : k_check<VA, VB, false, SEGCULL>, grid, K_THREADS, ctx->smem, ctx->stream, dependent, p);
+    if (p.wsplit > 1 && !count)                // few groups per CTA: several warps per group (planner-sized queries)
+        return launch_pdl(k_check<VA, VB, false, SEGCULL, true>, grid, K_THREADS, ctx->smem, ctx->stream, dependent, p);
+    return launch_pdl(count ? k_check<VA, VB, true, SEGCULL, false> : k_check<VA, VB, false, SEGCULL, false>, grid, K_THREADS, ctx->smem, ctx->stream, dependent, p);
 }
 
 template <int VA, int VB>
-static cudaError_t launch_check_seg(mpc_ctx *ctx, const KParams &p, int grid, bool dependent) {
+static cudaError_t launch_check_seg(mpc_ctx *ctx, const KParams &p, dim3 grid, bool dependent) {
     // steps with more than one block of 32 boundary segments get the instantiation with the segment sub-block culling
     // compiled in (the kernel is sensitive to its code size: C4, 4 segments, runs 5 % slower with it)
     return ctx->max_seg_step > 32 ? launch_check_vb<VA, VB, true>(ctx, p, grid, dependent) : launch_check_vb<VA, VB, false>(ctx, p, grid, dependent);
 }
 
-static cudaError_t launch_check_grid(mpc_ctx *ctx, const KParams &p, int grid, bool dependent) {
-    if (grid <= 0) return cudaSuccess;
+static cudaError_t launch_check_grid(mpc_ctx *ctx, const KParams &p, dim3 grid, bool dependent) {
+    if (grid.x == 0 || grid.y == 0) return cudaSuccess;
     const int va = ctx->VA, vb = ctx->VB;
     if (va == 4 && vb == 4) return launch_check_seg<4, 4>(ctx, p, grid, dependent);
     if (va == 4 && vb == 8) return launch_check_seg<4, 8>(ctx, p, grid, dependent);
@@ -894,25 +900,28 @@ static cudaError_t launch_check_grid(mpc_ctx *ctx, const KParams &p, int grid, b
 // `dependent`: the kernel right before this one in the stream is a kernel of the same step (k_clear)
 static cudaError_t launch_check(mpc_ctx *ctx, const KParams &p, bool dependent) {
     if (ctx->ctas == 0) return cudaSuccess;
-    const int scouts = std::min(ctx->scouts, ctx->J - 1);
-    if (scouts <= 0) return launch_check_grid(ctx, p, ctx->ctas, dependent);
-    // one launch per scout slot (finer chunks, nothing to look up yet / only the scouts before it), then the rest
+    const int L = std::max(1, ctx->scout_levels);
+    const int scouts = std::min(ctx->scouts, (ctx->J - 1) / L);
+    if (scouts <= 0) return launch_check_grid(ctx, p, dim3((unsigned)p.c_total, (unsigned)ctx->J), dependent);
+    // scout launches: finer chunks, every CTA walks `L` entries of the slot order with its own bits at hand; then the rest
     const char *qp = (const char *)ctx->qpack_d.p;
     for (int l = 0; l < scouts; l++) {
         KParams s = p;
-        s.slot_perm = p.slot_perm + l;
+        s.slot_perm = p.slot_perm + l * L;
         s.cta_tab = (const int2 *)(qp + ctx->qpack_cta2_off);
         s.gpc = ctx->scout_gpc;
         s.c_total = ctx->scout_c_total;
+        s.levels = L;
+        s.wsplit = 1;
         s.cross_exit = l > 0;
-        s.compact = (s.compact && s.gpc >= 32) ? 1 : 0;
-        cudaError_t e = launch_check_grid(ctx, s, ctx->scout_c_total, dependent || l > 0);
+        s.compact = (s.compact && (s.gpc >= p.cmin || L > 1)) ? 1 : 0;
+        cudaError_t e = launch_check_grid(ctx, s, dim3((unsigned)ctx->scout_c_total, 1u), dependent || l > 0);
         if (e != cudaSuccess) return e;
     }
     KParams m = p;
-    m.slot_perm = p.slot_perm + scouts;
+    m.slot_perm = p.slot_perm + scouts * L;
     m.cross_exit = 1;
-    return launch_check_grid(ctx, m, p.c_total * (ctx->J - scouts), true);
+    return launch_check_grid(ctx, m, dim3((unsigned)p.c_total, (unsigned)(ctx->J - scouts * L)), true);
 }
 
 // every instantiation of k_check may use the whole opt-in shared memory of the device (tiles of many-vertex polygons
@@ -922,10 +931,12 @@ static cudaError_t raise_smem_va_vb(int bytes) {
     cudaError_t e;
 #define MPC_RAISE(...) \
     if ((e = cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-    MPC_RAISE(k_check<VA, VB, false, false>)
-    MPC_RAISE(k_check<VA, VB, false, true>)
-    MPC_RAISE(k_check<VA, VB, true, false>)
-    MPC_RAISE(k_check<VA, VB, true, true>)
+    MPC_RAISE(k_check<VA, VB, false, false, false>)
+    MPC_RAISE(k_check<VA, VB, false, true, false>)
+    MPC_RAISE(k_check<VA, VB, true, false, false>)
+    MPC_RAISE(k_check<VA, VB, true, true, false>)
+    MPC_RAISE(k_check<VA, VB, false, false, true>)
+    MPC_RAISE(k_check<VA, VB, false, true, true>)
     MPC_RAISE(k_check_full<VA, VB, false>)
     MPC_RAISE(k_check_full<VA, VB, true>)
 #undef MPC_RAISE
@@ -957,7 +968,9 @@ static int launch_all(mpc_ctx *ctx, cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t 
     if (e1) CU(cudaEventRecord(e1, st));
     CU(launch_check(ctx, p, clear && !e1));
     if (e2) CU(cudaEventRecord(e2, st));
-    CU(launch_pdl(k_refine, std::max(1, ctx->prop.multiProcessorCount) * 8, 128, 0, st, !e2 && ctx->ctas > 0, p));     // one warp per item, 32 warps/SM
+    // one warp per work-list item / result word; a planner-sized batch has a handful of either: a small grid starts faster
+    const int rgrid = ctx->fused_clear ? 16 : std::max(1, ctx->prop.multiProcessorCount) * 8;
+    CU(launch_pdl(k_refine, dim3((unsigned)rgrid), 128, 0, st, !e2 && ctx->ctas > 0, p));
     return MPC_OK;
 }
 
@@ -1045,6 +1058,12 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
             ctas_per_slot(sg) * 8 >= resident)
             scouts = 1;
         if (const char *e = getenv("MPC_SCOUTS")) scouts = std::max(0, std::min(atoi(e), ctx->J - 1));      // tuning hook
+        // time slots a scout CTA walks through (latest first, then golden-ratio steps: every prefix of the order samples
+        // the horizon evenly, so a few levels see most of what can be seen)
+        int levels = std::min(4, std::max(1, (ctx->J - 1) / 2));
+        if (const char *e = getenv("MPC_SCOUT_LEVELS")) levels = std::max(1, atoi(e));                    // tuning hook
+        ctx->scout_levels = std::max(1, std::min(levels, ctx->J - 1));
+        scouts = std::min(scouts, (ctx->J - 1) / ctx->scout_levels);
         if (scouts && gpc == gpc_cap && gpc < GPC_MAX) {
             int gmax = 1;
             for (int q = 0; q < B; q++) gmax = std::max(gmax, (queries[q].cand_cnt + 31) / 32);
@@ -1057,7 +1076,7 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
     const int F = ob_fields(ctx->VB), FA = ob_fields(ctx->VA);
     ctx->cap_o = std::max(32, std::min((ctx->max_obst_step + 31) / 32 * 32, ctx->VB == 4 ? 320 : 160));
     ctx->cap_s = std::max(32, std::min((ctx->max_seg_step + 31) / 32 * 32, 512));
-    ctx->smem = 16 + 3 * GPC_MAX * 4 + (size_t)nwarps * QCAP * 4 + (size_t)nwarps * FA * 32 * 16 +
+    ctx->smem = 16 + 4 * GPC_MAX * 4 + (size_t)nwarps * QCAP * 4 + (size_t)nwarps * FA * 32 * 16 +
                 (size_t)ctx->cap_o * (F * 16 + 12) + (size_t)ctx->cap_s * 32;
     if (ctx->smem > ctx->prop.sharedMemPerBlockOptin)
         return fail(ctx, MPC_E_LIMIT, "tile of %zu bytes exceeds the device's shared memory", ctx->smem);
@@ -1122,6 +1141,12 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
     ctx->scouts = scouts; ctx->scout_gpc = sg; ctx->scout_c_total = (int)c2;
     ctas *= ctx->J;
     if (ctas > 0x7fffffffLL || words > 0x7fffffffLL) return fail(ctx, MPC_E_LIMIT, "batch too large");
+    // few groups per CTA and a grid that fits the machine at once (no early return across slots to coordinate): several
+    // warps per group, each with a share of the tile
+    ctx->wsplit = 1;
+    if (gpc <= 4 && scouts == 0 && ctas <= (long long)sms * K_MIN_CTAS && !(mode & (MPC_MODE_NO_CULL | MPC_MODE_COUNT_WORK)))
+        ctx->wsplit = gpc == 1 ? 8 : (gpc == 2 ? 4 : 2);
+    if (getenv("MPC_NO_WSPLIT")) ctx->wsplit = 1;                                              // tuning hook
     if (ncand) memcpy(hidx, cand_idx, bytes_i);
     ctx->maxabs_query = std::nextafter((float)maxq, INFINITY);
     hhdr[0] = ctx->maxabs_query;
@@ -1225,7 +1250,7 @@ static int run_once(mpc_ctx *ctx, float *ms, int *kernels, int *overflow, bool t
 // by one.  Graphs are keyed by everything that is baked into their nodes and dropped whenever a buffer moves.
 static int run_graph(mpc_ctx *ctx, float *ms, bool timed, bool sync = true) {
     const size_t bytes = sizeof(Counters) + (size_t)ctx->mask_words * sizeof(unsigned);
-    std::vector<long long> key = {(long long)ctx->B, (long long)ctx->ctas, (long long)ctx->scouts * 1000 + ctx->scout_gpc, (long long)ctx->scout_c_total, (long long)ctx->fused_clear, (long long)ctx->mask_words, (long long)ctx->mode,
+    std::vector<long long> key = {(long long)ctx->B, (long long)ctx->ctas, (long long)ctx->scouts * 1000 + ctx->scout_gpc + 100000LL * ctx->scout_levels + 10000000LL * ctx->wsplit, (long long)ctx->scout_c_total, (long long)ctx->fused_clear, (long long)ctx->mask_words, (long long)ctx->mode,
                                   (long long)ctx->gpc, (long long)ctx->cap_o, (long long)ctx->cap_s, (long long)ctx->smem,
                                   (long long)ctx->up_bytes, (long long)ctx->up_cand_bytes, (long long)ctx->wl_cap,
                                   (long long)ctx->VA, (long long)ctx->VB, (long long)ctx->ob_stride, (long long)ctx->sg_stride,

@@ -16,6 +16,9 @@ __all__ = ["CollisionEngine", "QUERY_DTYPE", "MODE_PLANNER", "MODE_VALIDATOR", "
            "MODE_COUNT_WORK", "MpcError", "make_queries", "unpack_mask"]
 
 
+_I4, _F8 = np.dtype(np.int32), np.dtype(np.float64)
+
+
 def _arr(a, dt):
     return np.ascontiguousarray(a, dtype=dt)
 
@@ -131,28 +134,39 @@ class CollisionEngine:
 
     @staticmethod
     def scene_args(scene_step_off, origins, step_obst_off, obst, obst_nv, step_seg_begin, step_seg_end, segs):
-        """checks the arrays and marshals them into the argument tuple of mpc_set_scenes (the arrays are kept alive by
-        the tuple).  A cycle that refills the same (page-locked) arrays every time marshals once and calls
-        set_scenes_args per cycle: the conversions and pointer look-ups cost ~40 us of interpreter time per call."""
-        scene_step_off = _arr(scene_step_off, np.int32)
+        """checks the arrays and marshals them into the argument tuple of mpc_set_scenes / mpc_submit (the arrays are
+        kept alive by the tuple).  Arrays that already have the dtype and layout of include/mpc.h are passed as they are
+        (a producer refilling page-locked buffers): ~10 us; anything else is converted first."""
+        def fit(a, dt, empty):
+            if a is None:
+                return np.zeros(empty, dt)
+            if type(a) is np.ndarray and a.dtype == dt and a.flags.c_contiguous:
+                return a
+            return np.ascontiguousarray(a, dtype=dt)
+
+        scene_step_off = fit(scene_step_off, _I4, 0)
         nscenes = len(scene_step_off) - 1
-        origins = _arr(origins, np.float64).reshape(nscenes, 2)
-        step_obst_off = _arr(step_obst_off, np.int32)
-        nsteps = int(scene_step_off[-1])
-        assert len(step_obst_off) == nsteps + 1
-        obst = _arr(obst if obst is not None else np.zeros((0, 4, 2)), np.float64)
+        origins = fit(origins, _F8, (0, 2))
+        step_obst_off = fit(step_obst_off, _I4, 0)
+        obst = fit(obst, _F8, (0, 4, 2))
         if obst.ndim != 3:
             obst = obst.reshape(-1, 4, 2)
-        obst_nv = _arr(obst_nv if obst_nv is not None else np.zeros(0), np.int32)
-        assert len(obst_nv) == obst.shape[0] == int(step_obst_off[-1])
-        step_seg_begin = _arr(step_seg_begin, np.int32)
-        step_seg_end = _arr(step_seg_end, np.int32)
-        assert len(step_seg_begin) == len(step_seg_end) == nsteps
-        segs = _arr(segs if segs is not None else np.zeros((0, 4)), np.float64).reshape(-1, 4)
+        obst_nv = fit(obst_nv, _I4, 0)
+        step_seg_begin = fit(step_seg_begin, _I4, 0)
+        step_seg_end = fit(step_seg_end, _I4, 0)
+        segs = fit(segs, _F8, (0, 4))
+        nsteps = int(scene_step_off[-1])
+        if not (origins.size == 2 * nscenes and len(step_obst_off) == nsteps + 1 and
+                len(obst_nv) == obst.shape[0] == int(step_obst_off[-1]) and
+                len(step_seg_begin) == len(step_seg_end) == nsteps and segs.size % 4 == 0):
+            raise AssertionError("inconsistent scene arrays: %d scenes, %d steps, step_obst_off %d, obst %s, obst_nv %d, "
+                                 "segment ranges %d / %d, segs %s" % (nscenes, nsteps, len(step_obst_off), obst.shape,
+                                                                      len(obst_nv), len(step_seg_begin), len(step_seg_end), segs.shape))
         keep = (scene_step_off, origins, step_obst_off, obst, obst_nv, step_seg_begin, step_seg_end, segs)
-        return (nscenes, _cabi.ptr(scene_step_off), _cabi.ptr(origins), _cabi.ptr(step_obst_off), _cabi.ptr(obst),
-                _cabi.ptr(obst_nv), int(obst.shape[1]), _cabi.ptr(step_seg_begin), _cabi.ptr(step_seg_end),
-                _cabi.ptr(segs), len(segs), keep)
+        ptr = _cabi.ptr
+        return (nscenes, ptr(scene_step_off), ptr(origins), ptr(step_obst_off), ptr(obst),
+                ptr(obst_nv), obst.shape[1], ptr(step_seg_begin), ptr(step_seg_end),
+                ptr(segs), segs.size // 4, keep)
 
     def set_scenes_args(self, args):
         self._scene_owner = None             # whoever staged through a PrimitiveChecker sets it again after this call
@@ -196,7 +210,8 @@ class CollisionEngine:
         """stage the scenes (`scene_args` = tuple of CollisionEngine.scene_args(...), or None to keep what is staged)
         and enqueue the query batch without waiting for the device; `wait()` returns its result.  Every array involved
         must stay alive and unchanged until then (this object keeps references)."""
-        queries = _arr(queries, QUERY_DTYPE)
+        if not (type(queries) is np.ndarray and queries.dtype == QUERY_DTYPE and queries.flags.c_contiguous):
+            queries = _arr(queries, QUERY_DTYPE)
         cand = _arr(cand_idx, np.int32) if cand_idx is not None else None
         if nw is None:
             nw = mask_words(queries)

@@ -52,7 +52,7 @@ class CollisionLanes:
         """page-locked copy; page-locked memory is visible to every context of the process"""
         return self.engines[0].pinned_like(array)
 
-    def run_cycles(self, cycles, mode=MODE_PLANNER, cand_idx=None, marshal_once=False, refill=None):
+    def run_cycles(self, cycles, mode=MODE_PLANNER, cand_idx=None, marshal_once=False, refill=None, want_stats=True):
         """cycles: sequence of (scene, queries); scene = dict with the arguments of CollisionEngine.set_scenes, or None
         to keep what the lane staged last.  Returns [(packed mask copy, stats dict)] in the order of `cycles`.
         Cycle i runs on lane i % lanes.
@@ -60,7 +60,8 @@ class CollisionLanes:
                       same page-locked arrays and guarantees their layout) instead of per cycle.
         refill:       optional callable(i, scene, queries) invoked right before cycle i is submitted -- the place where
                       a producer writes its new prediction into the (page-locked) arrays of that cycle; its time is
-                      part of the cycle."""
+                      part of the cycle.
+        want_stats:   False skips the per-cycle statistics record (the second element of every result is None)."""
         cycles = list(cycles)
         out = [None] * len(cycles)
         L = len(self.engines)
@@ -72,7 +73,7 @@ class CollisionLanes:
                 lane = i % L
                 eng = self.engines[lane]
                 if inflight[lane] is not None:
-                    out[inflight[lane]] = eng.wait()
+                    out[inflight[lane]] = eng.wait(want_stats)
                     inflight[lane] = None
                 if refill is not None:
                     refill(i, scene, queries)
@@ -88,7 +89,7 @@ class CollisionLanes:
                 inflight[lane] = i
             for lane in range(L):
                 if inflight[lane] is not None:
-                    out[inflight[lane]] = self.engines[lane].wait()
+                    out[inflight[lane]] = self.engines[lane].wait(want_stats)
                     inflight[lane] = None
         finally:
             for lane in range(L):                    # an exception above: drain what is still in flight

@@ -156,8 +156,8 @@ def aroc_shaped_problem(P=4096, T=10, O_lanes=8, slots=32, nqueries=8, lib_verts
     x = base["x"]                                                       # [P, T+1, 4]
     mid = 0.5 * (x[:, :-1, :] + x[:, 1:, :])                            # interval centre pose
     sweep = np.hypot(x[:, 1:, 0] - x[:, :-1, 0], x[:, 1:, 1] - x[:, :-1, 1])
-    ang = np.sort(rng.uniform(0, 2 * np.pi, (P, T, lib_verts)), axis=-1)
-    ang = ang + np.arange(lib_verts) * 1e-3                             # no coinciding vertices
+    # one vertex per angular stratum: strictly increasing, no coinciding vertices, no wrap-around
+    ang = 2 * np.pi * (np.arange(lib_verts) + rng.uniform(0.1, 0.9, (P, T, lib_verts))) / lib_verts
     a = (0.5 * LENGTH + 0.5 * sweep + 0.3)[..., None]                   # semi-axes: car + travelled distance + uncertainty
     b = (0.5 * WIDTH + 0.3)
     ex, ey = a * np.cos(ang), b * np.sin(ang)
