@@ -31,7 +31,9 @@ struct Counters {
     unsigned long long pairs_nominal, refined, exact_ties, near_tangent, parity_refined, cull_tests, axis_tests;
     unsigned wl_count;
     float tau;                   // the float32 error band the launch used (k_check block 0 reports it)
-    unsigned long long box_skipped, done_skipped, pad1[6];
+    unsigned long long box_skipped, done_skipped;
+    unsigned done_ctas, pad0;    // CTAs of k_check that have finished (single-kernel queries: the last one refines and publishes)
+    unsigned long long pad1[5];
 };
 
 struct KParams {
@@ -56,6 +58,12 @@ struct KParams {
     const float *maxabs_scene;
     // queries
     int c_total;                 // CTAs per time slot: the grid is (c_total, level groups), slot-major
+    int tail;                    // k_check<..., WS = true>: the last CTA to finish runs the refinement pass and copies the result
+                                 // block to host_res (page-locked, device-visible), then raises host_flag to host_seq
+    unsigned *host_res;
+    volatile unsigned *host_flag;
+    unsigned host_seq;
+    int res_words;               // 32-bit words of the result block the host wants (counters + caller-order mask)
     int wsplit;                  // k_check<..., WS = true>: warps per candidate group (2, 4 or 8)
     int levels;                  // time slots one CTA walks through in sequence (1: one slot per CTA; scout launches: several)
     int compact;                 // renumber the undecided candidates densely (needs: every library slot occupied, big CTAs)
@@ -75,6 +83,9 @@ struct KParams {
     unsigned mode;
     int gpc, cap_o, cap_s;
 };
+
+constexpr int REFINE_SCRATCH = 2 * (MPC_MAX_LIB_VERTS + MPC_MAX_OBST_VERTS);      // doubles of scratch per warp in refine_pass
+__device__ void refine_pass_smem(const KParams *ps, unsigned warp0, unsigned warps, double *pts);
 
 // ---------------------------------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + 1-D TMA bulk copy (global -> shared::cta)
@@ -583,7 +594,7 @@ constexpr int QCAP = 64;            // per-warp queue of (lane, record) pairs th
 // segments of the tile and the partial results (collision bits, crossing parity) are merged in shared memory.  Without it
 // seven of the eight warps of such a CTA idle while one walks the whole tile (2362 segments on the ZAM_ACC map).
 template <int VA, int VB, bool COUNT, bool SEGCULL, bool WS>
-__global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p) {
+__global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const __grid_constant__ KParams p) {
     constexpr int F = ob_fields(VB), FA = ob_fields(VA), NW = K_THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_raw);
@@ -1178,6 +1189,32 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const KParams p
             atomicAdd(&p.cnt->box_skipped, (unsigned long long)n_skip);
         }
     }
+    if (WS && p.tail) {
+        // Single-kernel query: the CTA that finishes last runs the float64 / exact pass over the work list (a handful
+        // of items for a planner-sized query) and writes the result block straight into page-locked host memory, then
+        // raises a flag the host is polling -- no k_refine launch, no copy node, no stream synchronisation to wake up
+        // from.
+        unsigned *s_is_last = reinterpret_cast<unsigned *>(smem_raw + 12);      // (bytes 0..7 mbarrier, 8..11 s_tot)
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) *s_is_last = atomicAdd(&p.cnt->done_ctas, 1u) == gridDim.x * gridDim.y - 1u;
+        __syncthreads();
+        if (*s_is_last) {
+            __threadfence();
+            KParams *ps = reinterpret_cast<KParams *>(s_ob);                 // (tile and polygon areas are free now)
+            for (int i = tid; i < (int)(sizeof(KParams) / 4); i += K_THREADS)
+                reinterpret_cast<unsigned *>(ps)[i] = reinterpret_cast<const unsigned *>(&p)[i];
+            __syncthreads();
+            refine_pass_smem(ps, (unsigned)warp, (unsigned)NW, reinterpret_cast<double *>(s_A) + warp * REFINE_SCRATCH);
+            __threadfence();
+            __syncthreads();
+            const unsigned *src = reinterpret_cast<const unsigned *>(p.cnt);
+            for (int i = tid; i < p.res_words; i += K_THREADS) p.host_res[i] = __ldcg(src + i);
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) *p.host_flag = p.host_seq;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1369,19 +1406,19 @@ __global__ void __launch_bounds__(K_THREADS, 2) k_check_full(const KParams p) {
 // so the lanes split them and votes put the answer together.  A single thread needs ~20 k cycles per polygon pair
 // (dependent float64 chains, local-memory polygon arrays); a warp needs ~1-2 k, which is what a planner that waits on
 // every query cares about.
-__global__ void __launch_bounds__(128, 8) k_refine(const KParams p) {
-    __shared__ double s_pts[4][2 * (MPC_MAX_LIB_VERTS + MPC_MAX_OBST_VERTS)];
-    pdl_wait();                  // everything here reads what k_check wrote
-    const unsigned n = min(p.cnt->wl_count, (unsigned)p.wl_cap);
-    const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const unsigned warps = (gridDim.x * blockDim.x) >> 5;
-    double *Ax = s_pts[wib], *Ay = Ax + MPC_MAX_LIB_VERTS, *Bx = Ay + MPC_MAX_LIB_VERTS, *By = Bx + MPC_MAX_OBST_VERTS;
+// `warp0` / `warps`: this warp's index among all warps that share the pass and their number; `pts`: scratch of
+// REFINE_SCRATCH doubles per warp in shared memory.  Called by k_refine (whole grid) and by the last CTA of a
+// single-kernel query (k_check<..., WS>).
+__device__ __forceinline__ void refine_pass(const KParams &p, const unsigned warp0, const unsigned warps, double *pts) {
+    const unsigned n = min(__ldcg(&p.cnt->wl_count), (unsigned)p.wl_cap);
+    const unsigned lane = threadIdx.x & 31;
+    double *Ax = pts, *Ay = Ax + MPC_MAX_LIB_VERTS, *Bx = Ay + MPC_MAX_LIB_VERTS, *By = Bx + MPC_MAX_OBST_VERTS;
     unsigned refined = 0, ties = 0, near_t = 0, par_ref = 0;
     const bool strict = p.mode & MPC_MODE_VALIDATOR;
     // phase A: result bits of spatially sorted candidate sets go home to the caller's candidate order.  One warp per
     // destination mask word: lane = candidate, which looks up its position in the sorted set and fetches its bit (a
     // gather: no atomics, no serial chain per word); one OR per word merges with the bits phase B adds below.
-    for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < (unsigned)p.nwords; w += warps) {
+    for (unsigned w = warp0; w < (unsigned)p.nwords; w += warps) {
         int lo = 0, hi = p.B;
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
@@ -1394,13 +1431,13 @@ __global__ void __launch_bounds__(128, 8) k_refine(const KParams p) {
         bool bit = false;
         if (ci < Q->cand_cnt) {
             const int sp = __ldg(p.cand_inv + Q->pos_base + ci);          // position of candidate ci in the sorted set
-            bit = (p.mask_sorted[Q->mask_off + (sp >> 5)] >> (sp & 31)) & 1u;
+            bit = (__ldcg(p.mask_sorted + Q->mask_off + (sp >> 5)) >> (sp & 31)) & 1u;
         }
         const unsigned word = __ballot_sync(FULL, bit);
         if (lane == 0 && word) atomicOr(p.mask + w, word);
     }
-    for (unsigned item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n; item += warps) {
-        const int4 e = p.wl[item];
+    for (unsigned item = warp0; item < n; item += warps) {
+        const int4 e = __ldcg(p.wl + item);
         const int q = e.x, ci = e.y, j = e.z & 0xffff, kind = e.z >> 16, obj = e.w;
         const QDev *Q = p.q + q;
         const int pj = p.cand[Q->cand_base + ci] * p.J + j;
@@ -1523,6 +1560,19 @@ __global__ void __launch_bounds__(128, 8) k_refine(const KParams p) {
         if (near_t) atomicAdd(&p.cnt->near_tangent, (unsigned long long)near_t);
         if (par_ref) atomicAdd(&p.cnt->parity_refined, (unsigned long long)par_ref);
     }
+}
+
+// out-of-line copy for the tail of k_check (its 64-register budget stays untouched).  The parameter block is handed over
+// in shared memory: a reference to the kernel parameters themselves would make the compiler copy all 1.3 KB of them
+// to every thread's stack.
+__device__ __noinline__ void refine_pass_smem(const KParams *ps, const unsigned warp0, const unsigned warps, double *pts) {
+    refine_pass(*ps, warp0, warps, pts);
+}
+
+__global__ void __launch_bounds__(128, 8) k_refine(const KParams p) {
+    __shared__ double s_pts[4][REFINE_SCRATCH];
+    pdl_wait();                  // everything here reads what k_check wrote
+    refine_pass(p, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5, s_pts[threadIdx.x >> 5]);
 }
 
 // clears the result block (counters + both mask arrays) at the head of a step; a kernel rather than a memset node so that

@@ -90,6 +90,8 @@ struct mpc_ctx {
     bool fused_clear = false;     // small result blocks are cleared by the zeros the query upload carries
     size_t qpack_cta_off = 0, qpack_cta2_off = 0, qpack_hdr_off = 0, up_bytes = 0, up_cand_bytes = 0, up_cand_src = 0;
     int wsplit = 1;               // warps per candidate group in k_check (few groups per CTA)
+    bool tail = false;            // prepared batch runs as ONE kernel: refinement + result hand-over in the last CTA of k_check
+    volatile unsigned *h_flag = nullptr;      // page-locked word the tail raises
     int scouts = 0, scout_gpc = 1, scout_c_total = 0, scout_levels = 1;      // leading time slots launched on their own (see launch_check)
     unsigned long long generation = 0;          // bumped whenever a pointer a captured graph holds may have changed
     std::map<std::vector<long long>, cudaGraphExec_t> graphs;
@@ -192,6 +194,8 @@ extern "C" int mpc_create(int device, mpc_ctx **out) {
     CU(ensure(ctx, ctx->res_d, sizeof(Counters) + 4096));
     CU(ensure(ctx, ctx->maxabs, 2 * sizeof(float)));       // [largest |coordinate| of the scenes, count of non-convex obstacle pieces]
     CU(cudaMemsetAsync(ctx->maxabs.p, 0, 2 * sizeof(float), ctx->stream));
+    CU(cudaMallocHost((void **)&ctx->h_flag, 64));
+    *ctx->h_flag = 0u;
     ctx->wl_cap = 1 << 18;
     if (const char *e = getenv("MPC_WL_CAP")) ctx->wl_cap = std::max(1, atoi(e));      // test hook: force the overflow path
     CU(ensure(ctx, ctx->wl, sizeof(int4) * (size_t)ctx->wl_cap));
@@ -220,6 +224,7 @@ extern "C" void mpc_destroy(mpc_ctx *ctx) {
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
     if (ctx->h_exp) cudaFreeHost(ctx->h_exp);
+    if (ctx->h_flag) cudaFreeHost((void *)ctx->h_flag);
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -838,6 +843,8 @@ static KParams make_params(mpc_ctx *ctx) {
     p.c_total = ctx->J > 0 ? ctx->ctas / ctx->J : 0;
     p.levels = 1;
     p.wsplit = ctx->wsplit;
+    p.tail = 0; p.host_res = (unsigned *)ctx->h_res; p.host_flag = ctx->h_flag; p.host_seq = 1u;
+    p.res_words = (int)((sizeof(Counters) + sizeof(unsigned) * (size_t)ctx->mask_words) / 4);
     p.cross_exit = ctx->ctas > ctx->prop.multiProcessorCount * K_MIN_CTAS;
     p.q = (const QDev *)qp; p.cta_tab = (const int2 *)(qp + ctx->qpack_cta_off); p.cand = (const int *)ctx->cand_d.p;
     p.cand_pos = (const int *)ctx->sets_pos.p;
@@ -954,8 +961,9 @@ static cudaError_t raise_smem_limits(const cudaDeviceProp &prop) {
     return raise_smem_va_vb<16, 8>(bytes);
 }
 
-static int launch_all(mpc_ctx *ctx, cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2, bool clear = true) {
+static int launch_all(mpc_ctx *ctx, cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2, bool clear = true, bool tail = false) {
     KParams p = make_params(ctx);
+    p.tail = tail ? 1 : 0;
     cudaStream_t st = ctx->stream;
     if (e0) CU(cudaEventRecord(e0, st));
     if (clear) {
@@ -968,8 +976,9 @@ static int launch_all(mpc_ctx *ctx, cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t 
     if (e1) CU(cudaEventRecord(e1, st));
     CU(launch_check(ctx, p, clear && !e1));
     if (e2) CU(cudaEventRecord(e2, st));
+    if (tail) return MPC_OK;          // the last CTA of k_check has refined and handed the result over
     // one warp per work-list item / result word; a planner-sized batch has a handful of either: a small grid starts faster
-    const int rgrid = ctx->fused_clear ? 16 : std::max(1, ctx->prop.multiProcessorCount) * 8;
+    const int rgrid = std::max(1, ctx->prop.multiProcessorCount) * (ctx->fused_clear ? 1 : 8);
     CU(launch_pdl(k_refine, dim3((unsigned)rgrid), 128, 0, st, !e2 && ctx->ctas > 0, p));
     return MPC_OK;
 }
@@ -1060,7 +1069,11 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
         if (const char *e = getenv("MPC_SCOUTS")) scouts = std::max(0, std::min(atoi(e), ctx->J - 1));      // tuning hook
         // time slots a scout CTA walks through (latest first, then golden-ratio steps: every prefix of the order samples
         // the horizon evenly, so a few levels see most of what can be seen)
-        int levels = std::min(4, std::max(1, (ctx->J - 1) / 2));
+        // Measured (C4 batch of 64, ms per batch at 1 / 2 / 3 / 4 / 6 / 8 levels): 0.1137 / 0.1125 / 0.1109 / 0.1151 / 0.1259 /
+        // 0.1399; the mixed regime loses 1.5 % at 2-3 levels.  What the later levels of a scout CTA gain in visibility they
+        // lose in parallelism (a quarter of the candidates is left after the first slot, the CTA still pays a tile fetch
+        // and two barriers per level), so the default stays at one level.
+        int levels = 1;
         if (const char *e = getenv("MPC_SCOUT_LEVELS")) levels = std::max(1, atoi(e));                    // tuning hook
         ctx->scout_levels = std::max(1, std::min(levels, ctx->J - 1));
         scouts = std::min(scouts, (ctx->J - 1) / ctx->scout_levels);
@@ -1147,6 +1160,11 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
     if (gpc <= 4 && scouts == 0 && ctas <= (long long)sms * K_MIN_CTAS && !(mode & (MPC_MODE_NO_CULL | MPC_MODE_COUNT_WORK)))
         ctx->wsplit = gpc == 1 ? 8 : (gpc == 2 ? 4 : 2);
     if (getenv("MPC_NO_WSPLIT")) ctx->wsplit = 1;                                              // tuning hook
+    // ... and such a batch with a small result block runs as ONE kernel (see the tail of k_check)
+    static const bool no_tail = getenv("MPC_NO_TAIL") != nullptr;
+    // (not on maps whose boundary needs several tiles per step: their work lists run to hundreds of items, too many for
+    // the eight warps of one CTA -- ZAM_ACC, 2362 segments: 62 us single-kernel vs 57 us with k_refine on all SMs)
+    ctx->tail = ctx->wsplit > 1 && fused && !no_tail && ctx->max_seg_step <= 512 && ctx->max_obst_step <= 320;
     if (ncand) memcpy(hidx, cand_idx, bytes_i);
     ctx->maxabs_query = std::nextafter((float)maxq, INFINITY);
     hhdr[0] = ctx->maxabs_query;
@@ -1250,7 +1268,8 @@ static int run_once(mpc_ctx *ctx, float *ms, int *kernels, int *overflow, bool t
 // by one.  Graphs are keyed by everything that is baked into their nodes and dropped whenever a buffer moves.
 static int run_graph(mpc_ctx *ctx, float *ms, bool timed, bool sync = true) {
     const size_t bytes = sizeof(Counters) + (size_t)ctx->mask_words * sizeof(unsigned);
-    std::vector<long long> key = {(long long)ctx->B, (long long)ctx->ctas, (long long)ctx->scouts * 1000 + ctx->scout_gpc + 100000LL * ctx->scout_levels + 10000000LL * ctx->wsplit, (long long)ctx->scout_c_total, (long long)ctx->fused_clear, (long long)ctx->mask_words, (long long)ctx->mode,
+    const bool tail = ctx->tail && ctx->ctas > 0;
+    std::vector<long long> key = {(long long)ctx->B, (long long)ctx->ctas, (long long)ctx->scouts * 1000 + ctx->scout_gpc + 100000LL * ctx->scout_levels + 10000000LL * ctx->wsplit, (long long)ctx->scout_c_total, (long long)ctx->fused_clear + 2 * (long long)tail, (long long)ctx->mask_words, (long long)ctx->mode,
                                   (long long)ctx->gpc, (long long)ctx->cap_o, (long long)ctx->cap_s, (long long)ctx->smem,
                                   (long long)ctx->up_bytes, (long long)ctx->up_cand_bytes, (long long)ctx->wl_cap,
                                   (long long)ctx->VA, (long long)ctx->VB, (long long)ctx->ob_stride, (long long)ctx->sg_stride,
@@ -1262,9 +1281,9 @@ static int run_graph(mpc_ctx *ctx, float *ms, bool timed, bool sync = true) {
         cudaGraph_t graph = nullptr;
         CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
         int rc = issue_uploads(ctx);
-        if (!rc) rc = launch_all(ctx, nullptr, nullptr, nullptr, !ctx->fused_clear);     // the upload just cleared it
+        if (!rc) rc = launch_all(ctx, nullptr, nullptr, nullptr, !ctx->fused_clear, tail);     // the upload just cleared it
         cudaError_t e1 = cudaSuccess;
-        if (!rc) e1 = cudaMemcpyAsync(ctx->h_res, ctx->res_p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        if (!rc && !tail) e1 = cudaMemcpyAsync(ctx->h_res, ctx->res_p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
         cudaError_t e2 = cudaStreamEndCapture(ctx->stream, &graph);
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (e1 != cudaSuccess || e2 != cudaSuccess) {
@@ -1277,19 +1296,33 @@ static int run_graph(mpc_ctx *ctx, float *ms, bool timed, bool sync = true) {
         if (e3 != cudaSuccess) return fail(ctx, MPC_E_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e3));
         it = ctx->graphs.emplace(key, exec).first;
     }
+    if (tail) *ctx->h_flag = 0u;
     if (timed) CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     CU(cudaGraphLaunch(it->second, ctx->stream));
     if (timed) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     if (!sync) return MPC_OK;
+    if (tail && !timed) {
+        // the last CTA raises the flag right after the result block has landed in host memory: watching that word is a
+        // few microseconds faster than waking up from a stream synchronisation
+        for (unsigned spins = 1; *ctx->h_flag == 0u; spins++) {
+            __builtin_ia32_pause();
+            if ((spins & 0xfffu) == 0u) {
+                const cudaError_t qe = cudaStreamQuery(ctx->stream);
+                if (qe == cudaSuccess) break;                                   // drained: the flag is up (or the launch did nothing)
+                if (qe != cudaErrorNotReady) return fail(ctx, MPC_E_CUDA, "query failed on the device: %s", cudaGetErrorString(qe));
+            }
+        }
+        if (*ctx->h_flag == 0u) CU(cudaStreamSynchronize(ctx->stream));
+        return MPC_OK;
+    }
     CU(cudaStreamSynchronize(ctx->stream));
     if (timed) CU(cudaEventElapsedTime(ms, ctx->ev[0], ctx->ev[1]));
     return MPC_OK;
 }
 
-// run the batch prepare_host() packed: graph replay for the common small-tile case, plain launches otherwise
 // after the graph of the batch has drained: grow the refinement list and re-run if it overflowed, hand out the result
 static int finish_batch(mpc_ctx *ctx, uint32_t *out_mask, int mask_words, mpc_stats *stats, float ms, bool timed) {
-    int kernels = (ctx->fused_clear ? 2 : 3) + ctx->scouts, overflow = 0, rc = MPC_OK;
+    int kernels = (ctx->fused_clear ? 2 : 3) + ctx->scouts - ((ctx->tail && ctx->ctas > 0) ? 1 : 0), overflow = 0, rc = MPC_OK;
     if (((const Counters *)ctx->h_res)->wl_count > (unsigned)ctx->wl_cap) {
         // refinement list overflowed: the plain path grows it and re-runs (and drops the graphs)
         rc = issue_uploads(ctx);
@@ -1530,6 +1563,7 @@ extern "C" int mpc_expand(mpc_ctx *ctx, int B, const mpc_query_desc *queries, co
         const size_t b_in = b_q + b_o + b_c, b_cost = sizeof(double) * (size_t)total, b_out = b_cost + sizeof(int) * (size_t)total;
         if (b_in + b_out > ctx->h_exp_cap) {
             if (ctx->h_exp) cudaFreeHost(ctx->h_exp);
+    if (ctx->h_flag) cudaFreeHost((void *)ctx->h_flag);
             ctx->h_exp = nullptr;
             ctx->h_exp_cap = 0;
             CU(cudaMallocHost(&ctx->h_exp, (b_in + b_out) * 2));

@@ -56,7 +56,7 @@ def test_expand_batches_match_the_oracle(MA, staged):
         assert np.array_equal(b0, b1)
         assert np.array_equal(c0, c1)                         # float64, identical operation order: bit for bit
         assert np.array_equal(g0, g1)
-        assert st['kernels'] >= 3
+        assert st['kernels'] >= 2                             # k_expand + k_check (single-kernel query: refinement in its tail)
         total += len(c0)
         hits += int((g0 >= 0).sum())
     assert total > 2000 and hits > 50
