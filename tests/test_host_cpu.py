@@ -244,9 +244,10 @@ def test_invalid_ring_detector_and_committed_count():
     assert len(hits) == 1 and hits[0][2] == 'cross'
     touch = np.array([[0, 0], [4, 0], [4, 2], [2, 0], [0, 2.0]])          # a vertex on a non-adjacent edge
     assert [h[2] for h in cir.self_intersections(touch)] == ['touch', 'touch']      # the two edges that meet in that vertex
-    pos, neg, minority, unc, cell = cir.lobe_areas(bow, [np.array([[1.0, -1], [3, -1], [3, 3], [1, 3]])], grid=200)
+    pos, neg, minority, unc, cell = cir.lobe_areas(bow, [np.array([[-1.0, -1], [3, -1], [3, 3], [-1, 3]])], grid=200)
     assert abs(pos - 1.0) < 0.05 and abs(neg - 1.0) < 0.05 and abs(minority - 1.0) < 0.05
-    assert unc < 0.6 * minority                                      # half of either lobe lies under the other polygon
+    assert unc == 0.0                                                # another polygon of the union covers both lobes
+    assert abs(cir.lobe_areas(bow, [square + 10.0], grid=200)[3] - minority) < 1e-12      # ... or none
     rep = json.load(open(os.path.join(os.path.dirname(__file__), "..", "profiles", "r02_invalid_rings.json")))
     assert rep["scenarios"] == 100 and rep["invalid_rings"] > 0
     assert rep["minority_lobe_area_not_covered_elsewhere_m2"] == 0.0
