@@ -57,7 +57,7 @@ struct KParams {
     int sg_stride;
     const float *maxabs_scene;
     // queries
-    int c_total;                 // CTAs per time slot: the grid is (c_total, level groups), slot-major
+    int c_total;                 // CTAs per time slot: the grid is (c_total, time slots), slot-major
     int tail;                    // k_check<..., WS = true>: the last CTA to finish runs the refinement pass and copies the result
                                  // block to host_res (page-locked, device-visible), then raises host_flag to host_seq
     unsigned *host_res;
@@ -65,7 +65,6 @@ struct KParams {
     unsigned host_seq;
     int res_words;               // 32-bit words of the result block the host wants (counters + caller-order mask)
     int wsplit;                  // k_check<..., WS = true>: warps per candidate group (2, 4 or 8)
-    int levels;                  // time slots one CTA walks through in sequence (1: one slot per CTA; scout launches: several)
     int compact;                 // renumber the undecided candidates densely (needs: every library slot occupied, big CTAs)
     int cmin;                    // ... in CTAs of at least this many groups (the pre-pass has to pay for itself)
     int cross_exit;              // grid larger than one resident wave: later time slots may use the bits of earlier ones
@@ -601,8 +600,8 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const __grid_co
     unsigned *s_coll = reinterpret_cast<unsigned *>(smem_raw + 16);
     unsigned *s_par = s_coll + GPC_MAX;
     unsigned *s_punc = s_par + GPC_MAX;
-    unsigned *s_donew = s_punc + GPC_MAX;                                      // collision words of the CTA's groups so far
-    unsigned *s_q = s_donew + GPC_MAX;                                         // [NW][QCAP]
+    unsigned *s_act = s_punc + GPC_MAX;                                        // WS: candidates of a group that hold an occupancy
+    unsigned *s_q = s_act + GPC_MAX;                                           // [NW][QCAP]
     float4 *s_A = reinterpret_cast<float4 *>(s_q + NW * QCAP);                 // [NW][FA][32] occupancy polygons
     float4 *s_ob = s_A + NW * FA * 32;                                         // [F][cap_o] obstacle records
     float *s_c = reinterpret_cast<float *>(s_ob + F * p.cap_o);                // circle x | y | -(r + rcull)^2
@@ -612,13 +611,12 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const __grid_co
     const unsigned lt_mask = (1u << lane) - 1u;
     const int WO = WS ? p.wsplit : 1;                 // warps per group
     const int wg = WS ? warp / WO : warp, wo = WS ? warp - wg * WO : 0, GW = WS ? NW / WO : NW;
-    unsigned *s_act = s_donew;                        // WS: candidates of the group that hold an occupancy (no done words there)
     pdl_trigger();                    // the next kernel of the step (main launch / k_refine) may start its own prologue
 
-    // which (slots, query, chunk) is this CTA.  The grid is SLOT-major: blockIdx.y counts groups of `levels` consecutive
-    // entries of the slot order, blockIdx.x the (query, chunk) pairs of the batch; CTAs start in index order, so by the
-    // time the later slots of a batch run, the earlier ones have published their collision bits and whole groups can
-    // return early (see `done` below).  (query, chunk) come from a table the host packs with the batch.
+    // which (slot, query, chunk) is this CTA.  The grid is SLOT-major: blockIdx.y counts the entries of the slot order,
+    // blockIdx.x the (query, chunk) pairs of the batch; CTAs start in index order, so by the time the later slots of a
+    // batch run, the earlier ones have published their collision bits and whole groups can return early (see `done`
+    // below).  (query, chunk) come from a table the host packs with the batch.
     const int2 ent = __ldg(p.cta_tab + blockIdx.x);
     const int q = ent.x;
     const QDev *Q = p.q + q;
@@ -647,20 +645,17 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const __grid_co
     unsigned *s_tot = reinterpret_cast<unsigned *>(smem_raw + 8);          // (the mbarrier uses bytes 0..7)
 
     if (tid == 0) mbar_init(bar, 1);
-    for (int i = tid; i < GPC_MAX; i += K_THREADS) s_donew[i] = 0;
     unsigned tile_no = 0;             // tiles fetched so far (CTA-uniform): parity of the mbarrier phase to wait for
     bool waited = false;              // pdl_wait() done (CTA-uniform)
-    bool loaded = false;              // s_donew holds the words earlier launches published (CTA-uniform)
 
-    // One time slot.  A CTA of a multi-level launch runs this for `levels` consecutive entries of the slot order and keeps
-    // the collision words of its candidates in shared memory in between: what an earlier slot decided is skipped at the
-    // later ones at once, without the round trip through the result words in L2 that separate CTAs need (and without the
-    // first-wave blindness of a slot-major grid: the CTAs of one wave cannot see each other's bits).
-    auto run_level = [&](const int lv) {
-    const int j = __ldg(p.slot_perm + blockIdx.y * p.levels + lv);
+    // (A variant in which a scout CTA walked several entries of the slot order in sequence, its candidates' collision
+    // words kept in shared memory in between, was built and measured: C4 batch 0.1137 / 0.1125 / 0.1109 / 0.1151 / 0.1399
+    // ms at 1 / 2 / 3 / 4 / 8 slots per CTA, mixed regime 1.5 % slower at 2-3, and the bookkeeping cost every launch
+    // 3.6 % -- removed again)
+    auto run_slot = [&]() {
+    const int j = __ldg(p.slot_perm + blockIdx.y);
     const int t = q_t0 + __ldg(p.slot_t + j);
-    if (lv > 0) __syncthreads();      // every warp is done with the previous slot: its tile, its group state, its s_donew updates
-    for (int i = tid; i < 3 * GPC_MAX; i += K_THREADS) s_coll[i] = 0;
+    for (int i = tid; i < 4 * GPC_MAX; i += K_THREADS) s_coll[i] = 0;
     __syncthreads();
     // reference guards: ind + time <= param['steps'] and ind + time < len(space)  (lowLevelPlannerManeuverAutomaton.py:120,122)
     if (t > q_limit || t < 0 || t >= q_nsteps) return;
@@ -673,8 +668,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const __grid_co
     // Everything above reads what the host staged before the step.  What follows reads the result words earlier launches
     // of the step publish (early return across time slots) or adds to the result block: a launch that looks at those
     // words waits for its predecessor here, one that does not waits only when its first tile has landed.
-    const bool xexit = (p.cross_exit || lv > 0) && !noexit;
-    const bool from_global = p.cross_exit && !loaded;      // first look: the words in L2, afterwards the CTA's own copy
+    const bool xexit = p.cross_exit && !noexit;
     if (xexit && !waited) { pdl_wait(); waited = true; }
 
     const int nphase = (nslot <= p.cap_o && nseg <= p.cap_s) ? 1 : max((nslot + p.cap_o - 1) / p.cap_o, (nseg + p.cap_s - 1) / p.cap_s);
@@ -686,9 +680,8 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const __grid_co
     // Compaction: when every library slot is occupied (so "candidate" = "occupancy present") and the step fits one tile,
     // the undecided candidates of the CTA are renumbered densely -- groups are formed from the live ones only, instead
     // of running every group that still has one straggler.  s_par / s_punc (multi-phase state, unused here) hold the
-    // live words and their running counts.  The pre-pass pays from ~32 groups on for a CTA that has to fetch its words
-    // from L2; at the later slots of a multi-level CTA they sit in shared memory and most groups are stragglers.
-    const bool cmode = !WS && xexit && p.compact && nphase == 1 && ng >= (lv > 0 ? 4 : p.cmin);
+    // live words and their running counts.  The pre-pass pays from ~32 groups on.
+    const bool cmode = !WS && xexit && p.compact && nphase == 1 && ng >= p.cmin;
     int total_live = 0;
     if (cmode) {
         if (warp == 0) {
@@ -700,9 +693,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const __grid_co
                 if (i < ng) {
                     const int nvalid = min(32, cand_cnt - (gbeg + i) * 32);
                     const unsigned valid = nvalid >= 32 ? FULL : ((1u << nvalid) - 1u);
-                    unsigned dw = s_donew[i];
-                    if (from_global) { dw |= __ldcg(maskp + gbeg + i); s_donew[i] = dw; }
-                    live = valid & ~dw;
+                    live = valid & ~__ldcg(maskp + gbeg + i);
                     s_live[i] = live;
                 }
                 cnt[r] = run;
@@ -729,7 +720,6 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const __grid_co
             if (lane == 31) *s_tot = incl;
         }
         __syncthreads();
-        if (from_global) loaded = true;
         total_live = (int)*s_tot;
         if (tid == 0) {                              // the statistic needs no library access here
             const unsigned long long w = (unsigned long long)min(ng * 32, cand_cnt - gbeg * 32) * (unsigned)(nobst + nseg);
@@ -741,15 +731,8 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const __grid_co
         bool live = false;
         for (int g = warp; g < ng; g += NW) {
             const int ci = (gbeg + g) * 32 + lane;
-            unsigned dw = s_donew[g];
-            if (from_global) {
-                dw |= __ldcg(maskp + gbeg + g);
-                __syncwarp();
-                if (lane == 0) s_donew[g] = dw;
-            }
-            if (ci < cand_cnt && !((dw >> lane) & 1u)) live = true;
+            if (ci < cand_cnt && !((__ldcg(maskp + gbeg + g) >> lane) & 1u)) live = true;
         }
-        if (from_global) loaded = true;
         if (!__syncthreads_or(live)) {
             unsigned skipped = 0;
             for (int g = warp; g < ng; g += NW) {
@@ -837,8 +820,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const __grid_co
                 // the same test per group: collision bits other time slots have published (L2, not L1).
                 // Every candidate of the group collides at another time step already: the reference returns at the
                 // first violation too (collision_check :124, collisionChecker.py:22,33).
-                done = s_donew[g];
-                if (p.cross_exit) done |= __ldcg(maskp + gbeg + g);      // what other CTAs have published meanwhile
+                done = __ldcg(maskp + gbeg + g);
                 if (__all_sync(FULL, !active || ((done >> lane) & 1u))) {
                     if (active && ph == 0) {
                         nom += (unsigned)(nobst + nseg);
@@ -1141,16 +1123,10 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const __grid_co
                 // spatially sorted candidate sets: bits in sorted order, k_refine moves them home
                 unsigned *out = (pos_base < 0 ? p.mask : p.mask_sorted) + Q->mask_off;
                 if (cmode) {    // compacted group: every lane has its own word
-                    if (coll && active) {
-                        atomicOr(out + (ci >> 5), 1u << (ci & 31));
-                        if (p.levels > 1) atomicOr(s_donew + ((ci >> 5) - gbeg), 1u << (ci & 31));
-                    }
+                    if (coll && active) atomicOr(out + (ci >> 5), 1u << (ci & 31));
                 } else {
                     unsigned word = __ballot_sync(FULL, coll && active);
-                    if (lane == 0 && word) {
-                        atomicOr(out + gbeg + g, word);
-                        if (p.levels > 1) s_donew[g] |= word;
-                    }
+                    if (lane == 0 && word) atomicOr(out + gbeg + g, word);
                 }
             }
         }
@@ -1172,9 +1148,9 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const __grid_co
             if (lane == 0 && word) atomicOr(out + gbeg + g, word);
         }
     }
-    };      // run_level
+    };      // run_slot
 
-    for (int lv = 0; lv < p.levels; lv++) run_level(lv);
+    run_slot();
     nom = __reduce_add_sync(FULL, nom);
     if (lane == 0 && nom) atomicAdd(&p.cnt->pairs_nominal, (unsigned long long)nom);
     if (COUNT) {

@@ -92,7 +92,7 @@ struct mpc_ctx {
     int wsplit = 1;               // warps per candidate group in k_check (few groups per CTA)
     bool tail = false;            // prepared batch runs as ONE kernel: refinement + result hand-over in the last CTA of k_check
     volatile unsigned *h_flag = nullptr;      // page-locked word the tail raises
-    int scouts = 0, scout_gpc = 1, scout_c_total = 0, scout_levels = 1;      // leading time slots launched on their own (see launch_check)
+    int scouts = 0, scout_gpc = 1, scout_c_total = 0;      // leading time slots launched on their own (see launch_check)
     unsigned long long generation = 0;          // bumped whenever a pointer a captured graph holds may have changed
     std::map<std::vector<long long>, cudaGraphExec_t> graphs;
     std::map<std::vector<long long>, cudaGraphExec_t> scene_graphs;      // staging of small scenes from pinned arrays
@@ -836,12 +836,11 @@ static KParams make_params(mpc_ctx *ctx) {
     // early return across time slots needs earlier slots to have finished: only grids beyond one resident wave
     // compaction of the undecided candidates costs a serial pre-pass per CTA: it pays from ~32 groups per CTA on
     // (C4, ms per batch of 4 / 8 / 16 / 64 queries: 0.073 / 0.085 / 0.111 / 0.219 with, 0.066 / 0.088 / 0.123 / 0.307 without)
-    p.compact = (ctx->lib_full && (ctx->gpc >= 32 || ctx->scout_levels > 1)) ? 1 : 0;
+    p.compact = (ctx->lib_full && ctx->gpc >= 32) ? 1 : 0;
     if (getenv("MPC_NO_COMPACT")) p.compact = 0;                                                // tuning hook
     p.cmin = 32;
     if (const char *e = getenv("MPC_CMODE_MIN")) { p.cmin = std::max(1, atoi(e)); if (ctx->lib_full) p.compact = 1; }      // tuning hook
     p.c_total = ctx->J > 0 ? ctx->ctas / ctx->J : 0;
-    p.levels = 1;
     p.wsplit = ctx->wsplit;
     p.tail = 0; p.host_res = (unsigned *)ctx->h_res; p.host_flag = ctx->h_flag; p.host_seq = 1u;
     p.res_words = (int)((sizeof(Counters) + sizeof(unsigned) * (size_t)ctx->mask_words) / 4);
@@ -907,28 +906,26 @@ static cudaError_t launch_check_grid(mpc_ctx *ctx, const KParams &p, dim3 grid, 
 // `dependent`: the kernel right before this one in the stream is a kernel of the same step (k_clear)
 static cudaError_t launch_check(mpc_ctx *ctx, const KParams &p, bool dependent) {
     if (ctx->ctas == 0) return cudaSuccess;
-    const int L = std::max(1, ctx->scout_levels);
-    const int scouts = std::min(ctx->scouts, (ctx->J - 1) / L);
+    const int scouts = std::min(ctx->scouts, ctx->J - 1);
     if (scouts <= 0) return launch_check_grid(ctx, p, dim3((unsigned)p.c_total, (unsigned)ctx->J), dependent);
-    // scout launches: finer chunks, every CTA walks `L` entries of the slot order with its own bits at hand; then the rest
+    // one launch per scout slot (finer chunks, nothing to look up yet / only the scouts before it), then the rest
     const char *qp = (const char *)ctx->qpack_d.p;
     for (int l = 0; l < scouts; l++) {
         KParams s = p;
-        s.slot_perm = p.slot_perm + l * L;
+        s.slot_perm = p.slot_perm + l;
         s.cta_tab = (const int2 *)(qp + ctx->qpack_cta2_off);
         s.gpc = ctx->scout_gpc;
         s.c_total = ctx->scout_c_total;
-        s.levels = L;
         s.wsplit = 1;
         s.cross_exit = l > 0;
-        s.compact = (s.compact && (s.gpc >= p.cmin || L > 1)) ? 1 : 0;
+        s.compact = (s.compact && s.gpc >= p.cmin) ? 1 : 0;
         cudaError_t e = launch_check_grid(ctx, s, dim3((unsigned)ctx->scout_c_total, 1u), dependent || l > 0);
         if (e != cudaSuccess) return e;
     }
     KParams m = p;
-    m.slot_perm = p.slot_perm + scouts * L;
+    m.slot_perm = p.slot_perm + scouts;
     m.cross_exit = 1;
-    return launch_check_grid(ctx, m, dim3((unsigned)p.c_total, (unsigned)(ctx->J - scouts * L)), true);
+    return launch_check_grid(ctx, m, dim3((unsigned)p.c_total, (unsigned)(ctx->J - scouts)), true);
 }
 
 // every instantiation of k_check may use the whole opt-in shared memory of the device (tiles of many-vertex polygons
@@ -1067,16 +1064,6 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
             ctas_per_slot(sg) * 8 >= resident)
             scouts = 1;
         if (const char *e = getenv("MPC_SCOUTS")) scouts = std::max(0, std::min(atoi(e), ctx->J - 1));      // tuning hook
-        // time slots a scout CTA walks through (latest first, then golden-ratio steps: every prefix of the order samples
-        // the horizon evenly, so a few levels see most of what can be seen)
-        // Measured (C4 batch of 64, ms per batch at 1 / 2 / 3 / 4 / 6 / 8 levels): 0.1137 / 0.1125 / 0.1109 / 0.1151 / 0.1259 /
-        // 0.1399; the mixed regime loses 1.5 % at 2-3 levels.  What the later levels of a scout CTA gain in visibility they
-        // lose in parallelism (a quarter of the candidates is left after the first slot, the CTA still pays a tile fetch
-        // and two barriers per level), so the default stays at one level.
-        int levels = 1;
-        if (const char *e = getenv("MPC_SCOUT_LEVELS")) levels = std::max(1, atoi(e));                    // tuning hook
-        ctx->scout_levels = std::max(1, std::min(levels, ctx->J - 1));
-        scouts = std::min(scouts, (ctx->J - 1) / ctx->scout_levels);
         if (scouts && gpc == gpc_cap && gpc < GPC_MAX) {
             int gmax = 1;
             for (int q = 0; q < B; q++) gmax = std::max(gmax, (queries[q].cand_cnt + 31) / 32);
@@ -1269,7 +1256,7 @@ static int run_once(mpc_ctx *ctx, float *ms, int *kernels, int *overflow, bool t
 static int run_graph(mpc_ctx *ctx, float *ms, bool timed, bool sync = true) {
     const size_t bytes = sizeof(Counters) + (size_t)ctx->mask_words * sizeof(unsigned);
     const bool tail = ctx->tail && ctx->ctas > 0;
-    std::vector<long long> key = {(long long)ctx->B, (long long)ctx->ctas, (long long)ctx->scouts * 1000 + ctx->scout_gpc + 100000LL * ctx->scout_levels + 10000000LL * ctx->wsplit, (long long)ctx->scout_c_total, (long long)ctx->fused_clear + 2 * (long long)tail, (long long)ctx->mask_words, (long long)ctx->mode,
+    std::vector<long long> key = {(long long)ctx->B, (long long)ctx->ctas, (long long)ctx->scouts * 1000 + ctx->scout_gpc + 10000000LL * ctx->wsplit, (long long)ctx->scout_c_total, (long long)ctx->fused_clear + 2 * (long long)tail, (long long)ctx->mask_words, (long long)ctx->mode,
                                   (long long)ctx->gpc, (long long)ctx->cap_o, (long long)ctx->cap_s, (long long)ctx->smem,
                                   (long long)ctx->up_bytes, (long long)ctx->up_cand_bytes, (long long)ctx->wl_cap,
                                   (long long)ctx->VA, (long long)ctx->VB, (long long)ctx->ob_stride, (long long)ctx->sg_stride,
