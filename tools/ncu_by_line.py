@@ -5,8 +5,10 @@
     ncu -i rep.ncu-rep --page source --csv > src.csv
     python tools/ncu_by_line.py all.sass src.csv '<mangled kernel name>' [--regions a-b:name,...]
 
-Every instruction is charged to the OUTERMOST line of its inline chain that lies inside the kernel (so helper code is
-charged to its call site in the kernel)."""
+Every instruction is charged to the OUTERMOST line of its inline chain that lies inside the kernel body (so helper code
+is charged to its call site in the kernel).  --range=a-b gives the body's line range (frames outside it -- the
+__global__ wrapper that inlines the body -- are skipped), --exclude=n,m lines that are mere call sites of the body's
+own top-level lambda."""
 import collections
 import csv
 import re
@@ -16,6 +18,12 @@ import sys
 def main():
     sass, src, kern = sys.argv[1:4]
     regions = []
+    lo_hi, exclude = None, set()
+    for a in sys.argv[4:]:
+        if a.startswith('--range='):
+            lo_hi = tuple(int(v) for v in a[len('--range='):].split('-'))
+        if a.startswith('--exclude='):
+            exclude = set(int(v) for v in a[len('--exclude='):].split(',') if v)
     for a in sys.argv[4:]:
         if a.startswith('--regions='):
             for item in a[len('--regions='):].split(','):
@@ -38,8 +46,13 @@ def main():
             if pending:
                 chain = pending
                 pending = []
-            outer = chain[-1][1] if chain and chain[-1][1] is not None else (chain[-1][0] if chain else 0)
-            # walk: the last entry of the chain is the outermost frame
+            frames = ([chain[0][0]] + [c[1] for c in chain if c[1] is not None]) if chain else [0]
+            outer = frames[-1]
+            if lo_hi is not None:       # the last entry of the chain is the outermost frame: walk inwards to the body
+                for f in reversed(frames):
+                    if lo_hi[0] <= f <= lo_hi[1] and f not in exclude:
+                        outer = f
+                        break
             inst[int(m.group(1), 16)] = (outer, chain[0][0] if chain else 0, m.group(2))
     rows = list(csv.reader(open(src)))
     hdr, data = rows[1], rows[2:]
