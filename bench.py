@@ -527,15 +527,18 @@ def main():
     # every lane owns page-locked arrays the producer refills before each cycle; NPOSE distinct predictions (the scene
     # shifted by a few centimetres) and pose sets rotate through them
     variants = [scene["obst"] + np.array([0.03 * v, 0.0]) for v in range(NPOSE)]
+    # two sets of page-locked buffers per lane: with a producer thread (second figure) buffer i % (2 lanes) is refilled
+    # while the cycle that used it `lanes` cycles ago is long done and the previous cycle is being submitted
+    NBUF = 2 * lanes
     lane_scene = []
-    for _ in range(lanes):
+    for _ in range(NBUF):
         d = dict(scene, origins=origins)
         for k in skeys:
             d[k] = pool.pinned_like(np.ascontiguousarray(d[k]))
         lane_scene.append(d)
-    lane_q = [pool.pinned_like(poses[0]) for _ in range(lanes)]
+    lane_q = [pool.pinned_like(poses[0]) for _ in range(NBUF)]
     ncycles = args.steps * K
-
+    nw_batch = nq * ((P + 31) // 32)
     pose_bytes = [x.view(np.uint8) for x in poses]
 
     def refill(i, sc, q):
@@ -543,15 +546,73 @@ def main():
         np.copyto(q.view(np.uint8), pose_bytes[(i // NPOSE) % NPOSE])      # (a record-wise copy of the 4 KB costs 10 us)
 
     def cycles_for(n):
-        return [(lane_scene[i % lanes], lane_q[i % lanes]) for i in range(n)]
+        return [(lane_scene[i % NBUF], lane_q[i % NBUF]) for i in range(n)]
 
     mode_e2e = MODE_PLANNER | MODE_NO_TIMING
-    pool.run_cycles(cycles_for(args.warmup * lanes * 2), mode_e2e, refill=refill, want_stats=False)
+    pool.run_cycles(cycles_for(args.warmup * lanes * 2), mode_e2e, refill=refill, want_stats=False, mask_words_hint=nw_batch)
     barrier()
     t0 = time.perf_counter()
-    res = pool.run_cycles(cycles_for(ncycles), mode_e2e, refill=refill, want_stats=False)
+    res = pool.run_cycles(cycles_for(ncycles), mode_e2e, refill=refill, want_stats=False, mask_words_hint=nw_batch)
     barrier()
     e2e_s = time.perf_counter() - t0
+
+    # the same with the producer on its own thread (numpy releases the interpreter lock for the copy): cycle i + 1 is
+    # written while cycle i is marshalled and submitted
+    class Producer(threading.Thread):
+        def __init__(self):
+            super().__init__(daemon=True)
+            self.todo, self.done = [], {}
+            self.cv = threading.Condition()
+            self.stop = False
+
+        def run(self):
+            while True:
+                with self.cv:
+                    while not self.todo and not self.stop:
+                        self.cv.wait()
+                    if self.stop:
+                        return
+                    i, sc, q = self.todo.pop(0)
+                refill(i, sc, q)
+                with self.cv:
+                    self.done[i] = True
+                    self.cv.notify_all()
+
+        def ask(self, i, sc, q):
+            with self.cv:
+                self.todo.append((i, sc, q))
+                self.cv.notify_all()
+
+        def get(self, i):
+            with self.cv:
+                while i not in self.done:
+                    self.cv.wait()
+                del self.done[i]
+
+    def run_with_producer(n):
+        prod = Producer()
+        prod.start()
+        cyc = cycles_for(n)
+        prod.ask(0, *cyc[0])
+
+        def handoff(i, sc, q):
+            prod.get(i)                       # this cycle's prediction is in its buffers
+            if i + 1 < n:
+                prod.ask(i + 1, *cyc[i + 1])  # the next one is written while this one is marshalled and submitted
+        out = pool.run_cycles(cyc, mode_e2e, refill=handoff, want_stats=False, mask_words_hint=nw_batch)
+        with prod.cv:
+            prod.stop = True
+            prod.cv.notify_all()
+        return out
+
+    run_with_producer(args.warmup * lanes * 2)
+    barrier()
+    t0 = time.perf_counter()
+    res_p = run_with_producer(ncycles)
+    barrier()
+    e2e_prod_s = time.perf_counter() - t0
+    if not all(np.array_equal(a[0], b[0]) for a, b in zip(res[-NBUF:], res_p[-NBUF:])):
+        raise SystemExit("bench.py: producer-thread run and single-thread run disagree")
     # check the last cycles against a synchronous single-context run of the same inputs
     for i in range(ncycles - lanes, ncycles):
         sc_i = dict(pscene)
@@ -564,10 +625,10 @@ def main():
     for lsc, lq in zip(lane_scene, lane_q):
         np.copyto(lsc["obst"], variants[0])
         np.copyto(lq, poses[0])
-    pool.run_cycles(cycles_for(lanes * 2), mode_e2e, marshal_once=True, want_stats=False)
+    pool.run_cycles(cycles_for(lanes * 2), mode_e2e, marshal_once=True, want_stats=False, mask_words_hint=nw_batch)
     barrier()
     t0 = time.perf_counter()
-    pool.run_cycles(cycles_for(ncycles), mode_e2e, marshal_once=True, want_stats=False)
+    pool.run_cycles(cycles_for(ncycles), mode_e2e, marshal_once=True, want_stats=False, mask_words_hint=nw_batch)
     barrier()
     e2e_cached_s = time.perf_counter() - t0
     pool.close()
@@ -592,7 +653,7 @@ def main():
     c5 = c5_block(local, rank, world, barrier, min(lanes, 3), check=(world == 1 and not args.no_cpu_baseline))
 
     # ---- reduce over ranks (max time), gather the result bitmasks -----------------------------------------------------
-    times = torch.tensor([dev_s, e2e_s, wall, e2e_serial_s, e2e_cached_s, c5["dev_s"], c5["e2e_s"]], dtype=torch.float64, device="cuda")
+    times = torch.tensor([dev_s, e2e_s, wall, e2e_serial_s, e2e_cached_s, c5["dev_s"], c5["e2e_s"], e2e_prod_s], dtype=torch.float64, device="cuda")
     sums = torch.tensor([float(len(collide) - int(collide.sum())), c5["pairs"], c5["cand"], c5["coll"], c5["refined"], c5["near"],
                          float(c5["h2d"])], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -600,7 +661,7 @@ def main():
         masks = [torch.empty(len(mask), dtype=torch.int32, device="cuda") for _ in range(world)] if rank == 0 else None
         dist.gather(torch.from_numpy(mask.view(np.int32)).cuda(), masks, dst=0)      # only result bitmasks travel
         dist.all_reduce(sums)
-    dev_s, e2e_s, wall, e2e_serial_s, e2e_cached_s, c5_dev_s, c5_e2e_s = [float(x) for x in times.cpu()]
+    dev_s, e2e_s, wall, e2e_serial_s, e2e_cached_s, c5_dev_s, c5_e2e_s, e2e_prod_s = [float(x) for x in times.cpu()]
     nfree, c5_pairs, c5_cand, c5_coll, c5_refined, c5_near, c5_h2d = [float(x) for x in sums.cpu()]
 
     if rank == 0:
@@ -670,6 +731,9 @@ def main():
                             "per GPU): every cycle the producer's new prediction is copied into the lane's page-locked "
                             "arrays (819 KB memcpy), the arguments are marshalled anew, scene + poses go host -> device, "
                             "the packed mask comes back; wall clock over %d cycles" % (lanes, ncycles),
+                    "producer_thread": {"value": world * ncycles * checks_batch / e2e_prod_s, "ms_per_batch": 1e3 * e2e_prod_s / ncycles,
+                                        "what": "same cycles, the producer's memcpy on a second host thread (double-buffered "
+                                                "page-locked arrays): the calling thread only marshals, submits and waits"},
                     "cached_pointers": {"value": world * ncycles * checks_batch / e2e_cached_s, "ms_per_batch": 1e3 * e2e_cached_s / ncycles,
                                         "what": "same arrays every cycle, marshalled once (round 1's e2e definition)"},
                     "single_context": {"value": world * ncycles * checks_batch / e2e_serial_s,

@@ -1344,6 +1344,8 @@ extern "C" int mpc_submit(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_o
                           int B, const mpc_query_desc *queries, const int32_t *cand_idx, int ncand, unsigned mode) {
     if (!ctx || !ctx->stream) return MPC_E_STATE;
     if (ctx->pending) return fail(ctx, MPC_E_STATE, "a submitted batch is waiting for mpc_wait");
+    static const bool dbg_t = getenv("MPC_DEBUG_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     int rc = MPC_OK;
     ctx->pending_scenes = false;
     if (nscenes > 0) {
@@ -1352,10 +1354,18 @@ extern "C" int mpc_submit(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_o
         if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
         ctx->pending_scenes = true;
     }
+    const auto t1 = std::chrono::steady_clock::now();
     rc = prepare_host(ctx, B, queries, cand_idx, ncand, mode | MPC_MODE_NO_TIMING, false);
+    const auto t2 = std::chrono::steady_clock::now();
     float ms = 0.f;
     if (!rc) rc = run_graph(ctx, &ms, false, false);
     if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
+    if (dbg_t) {
+        const auto t3 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[mpc submit] scenes %.1f us, pack %.1f us, graph launch %.1f us\n",
+                std::chrono::duration<double, std::micro>(t1 - t0).count(), std::chrono::duration<double, std::micro>(t2 - t1).count(),
+                std::chrono::duration<double, std::micro>(t3 - t2).count());
+    }
     ctx->pending = true;
     return MPC_OK;
 }

@@ -52,7 +52,8 @@ class CollisionLanes:
         """page-locked copy; page-locked memory is visible to every context of the process"""
         return self.engines[0].pinned_like(array)
 
-    def run_cycles(self, cycles, mode=MODE_PLANNER, cand_idx=None, marshal_once=False, refill=None, want_stats=True):
+    def run_cycles(self, cycles, mode=MODE_PLANNER, cand_idx=None, marshal_once=False, refill=None, want_stats=True,
+                   mask_words_hint=None):
         """cycles: sequence of (scene, queries); scene = dict with the arguments of CollisionEngine.set_scenes, or None
         to keep what the lane staged last.  Returns [(packed mask copy, stats dict)] in the order of `cycles`.
         Cycle i runs on lane i % lanes.
@@ -61,7 +62,9 @@ class CollisionLanes:
         refill:       optional callable(i, scene, queries) invoked right before cycle i is submitted -- the place where
                       a producer writes its new prediction into the (page-locked) arrays of that cycle; its time is
                       part of the cycle.
-        want_stats:   False skips the per-cycle statistics record (the second element of every result is None)."""
+        want_stats:   False skips the per-cycle statistics record (the second element of every result is None).
+        mask_words_hint: number of result words of every cycle's batch when the caller knows it (all cycles ask for the
+                      same candidate counts); counting them from the query records costs ~6 us per cycle."""
         cycles = list(cycles)
         out = [None] * len(cycles)
         L = len(self.engines)
@@ -85,7 +88,7 @@ class CollisionLanes:
                             args = cache[id(scene)] = CollisionEngine.scene_args(*[scene[k] for k in SCENE_KEYS])
                     else:
                         args = CollisionEngine.scene_args(*[scene[k] for k in SCENE_KEYS])
-                eng.submit(args, queries, mode, cand)
+                eng.submit(args, queries, mode, cand, mask_words_hint)
                 inflight[lane] = i
             for lane in range(L):
                 if inflight[lane] is not None:
