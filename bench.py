@@ -77,7 +77,7 @@ def ncu_summary():
 def kernel_source_hash():
     import hashlib
     h = hashlib.sha256()
-    for f in ("mpc_device.cuh", "mpc_kernels.cu", "mpc_exact.cuh"):
+    for f in ("mpc_device.cuh", "mpc_exact.cuh", "mpc_expand.cuh"):      # the device code
         h.update(open(os.path.join(ROOT, "motionplanner_b200", "csrc", f), "rb").read())
     return h.hexdigest()[:16]
 
@@ -545,8 +545,8 @@ def main():
         np.copyto(sc["obst"], variants[i % NPOSE])        # the new prediction of this cycle (819 KB memcpy, counted)
         np.copyto(q.view(np.uint8), pose_bytes[(i // NPOSE) % NPOSE])      # (a record-wise copy of the 4 KB costs 10 us)
 
-    def cycles_for(n):
-        return [(lane_scene[i % NBUF], lane_q[i % NBUF]) for i in range(n)]
+    def cycles_for(n, nbuf=lanes):
+        return [(lane_scene[i % nbuf], lane_q[i % nbuf]) for i in range(n)]
 
     mode_e2e = MODE_PLANNER | MODE_NO_TIMING
     pool.run_cycles(cycles_for(args.warmup * lanes * 2), mode_e2e, refill=refill, want_stats=False, mask_words_hint=nw_batch)
@@ -592,7 +592,7 @@ def main():
     def run_with_producer(n):
         prod = Producer()
         prod.start()
-        cyc = cycles_for(n)
+        cyc = cycles_for(n, NBUF)
         prod.ask(0, *cyc[0])
 
         def handoff(i, sc, q):
@@ -611,7 +611,7 @@ def main():
     res_p = run_with_producer(ncycles)
     barrier()
     e2e_prod_s = time.perf_counter() - t0
-    if not all(np.array_equal(a[0], b[0]) for a, b in zip(res[-NBUF:], res_p[-NBUF:])):
+    if not all(np.array_equal(a[0], b[0]) for a, b in zip(res[-lanes:], res_p[-lanes:])):
         raise SystemExit("bench.py: producer-thread run and single-thread run disagree")
     # check the last cycles against a synchronous single-context run of the same inputs
     for i in range(ncycles - lanes, ncycles):

@@ -74,7 +74,7 @@ def short(k):
 def summary(tag, folder):
     import hashlib
     h = hashlib.sha256()
-    for f in ("mpc_device.cuh", "mpc_kernels.cu", "mpc_exact.cuh"):
+    for f in ("mpc_device.cuh", "mpc_exact.cuh", "mpc_expand.cuh"):      # the device code
         h.update(open(os.path.join(ROOT, "motionplanner_b200", "csrc", f), "rb").read())
     out = {"capture": tag, "kernel_source_hash": h.hexdigest()[:16],
            "how": "tools/capture_r02.sh under gpurun: ncu --set full --clock-control none on tools/ncu_target.py <regime> 2; "
