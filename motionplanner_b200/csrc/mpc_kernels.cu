@@ -12,7 +12,7 @@
 //   k_stage_obst / k_stage_segs   float64 global-frame inputs -> scene-local float32 SoA records (vertex pairs, unit
 //                                 edge lines, quad-packed bounding circles, one box per block of 32 segments) in
 //                                 32-aligned slot ranges per time step; CCW-normalised float64 copy for the tie-break.
-//   k_check<VA,VB,COUNT,NOCULL>   one CTA (8 warps) per (query, occupancy slot, chunk of candidate groups).  The
+//   k_check<VA,VB,COUNT,SEGCULL,WS>   one CTA (8 warps) per (query, occupancy slot, chunk of candidate groups).  The
 //                                 obstacle and boundary-segment records of that time step are brought into shared
 //                                 memory with one TMA bulk copy per field (cp.async.bulk + mbarrier).  A warp works on
 //                                 32 candidate primitives at a time, lane = primitive: it transforms the occupancy
@@ -21,10 +21,16 @@
 //                                 FADD2/FFMA2, two obstacles per instruction; the pairs it cannot separate are queued
 //                                 per warp and the full separating-axis test runs on 32 queued pairs at once.  A tile
 //                                 ends as soon as __all_sync says every lane has collided; __ballot_sync assembles the
-//                                 32 result bits that are OR-ed into the packed mask.
+//                                 32 result bits that are OR-ed into the packed mask.  WS (planner-sized batches):
+//                                 several warps per candidate group, each with a share of the tile; the last CTA to
+//                                 finish refines the work list and hands the result block to the host.
+//   k_check_full<VA,VB,COUNT>     MPC_MODE_NO_CULL: every nominal pair runs the complete test, two polygons per lane.
 //   k_refine                      float64 / exact re-decision of the pairs inside the float32 error band, one warp per
 //                                 pair (lanes over the orientation tests).
-// mpc_query replays the sequence (H2D, clear, k_check, k_refine, D2H) as one instantiated CUDA graph per batch shape.
+// A step = k_clear -> k_check (scout launch + main launch for big batches) -> k_refine, chained as programmatic
+// dependent launches; mpc_query replays (H2D, the chain, D2H) as one instantiated CUDA graph per batch shape,
+// planner-sized batches as (H2D, one k_check<..., WS> launch) with the host polling a page-locked flag;
+// mpc_submit / mpc_wait enqueue and collect a cycle (scene staging + query) without blocking in between.
 #include <cuda_runtime.h>
 
 #include <algorithm>
