@@ -5,7 +5,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmpcheck.so")
+# MPC_LIB_PATH selects another build of the same library (csrc/libmpcheck_dbg.so: device asserts, `make debug`)
+LIB_PATH = os.environ.get("MPC_LIB_PATH") or os.path.join(_HERE, "csrc", "libmpcheck.so")
 
 MODE_PLANNER = 0
 MODE_VALIDATOR = 1

@@ -9,6 +9,15 @@
 #include "../../include/mpc.h"
 #include "mpc_exact.cuh"
 
+// index invariants of the kernels, compiled in by `make debug` (-DMPC_DEBUG_ASSERTS; libmpcheck_dbg.so, selected with
+// MPC_LIB_PATH): compute-sanitizer is not available on the measurement pool, the parity suites run against this build instead
+#ifdef MPC_DEBUG_ASSERTS
+#include <cassert>
+#define MPC_ASSERT(c) assert(c)
+#else
+#define MPC_ASSERT(c) ((void)0)
+#endif
+
 namespace mpc {
 
 constexpr float BIG = 1e30f;
@@ -755,6 +764,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const __grid_co
         const int sc0 = ph * p.cap_s, scn = max(0, min(nseg - sc0, p.cap_s));
         const bool loading = (ocn | scn) != 0;
         if (tid == 0 && loading) {
+            MPC_ASSERT(ocn <= p.cap_o && scn <= p.cap_s && (ocn & 31) == 0 && o0 + oc0 + ocn <= p.ob_stride && (!scn || g0 + sc0 + scn <= p.sg_stride));
             mbar_expect_tx(bar, (unsigned)(ocn * (16 * F + 12) + scn * 32));
             if (ocn) {
                 for (int f = 0; f < F; f++)
@@ -797,7 +807,9 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const __grid_co
                     const int mid = (lo + hi) >> 1;
                     if ((int)s_pref[mid] <= rk) lo = mid; else hi = mid;
                 }
+                MPC_ASSERT(!active || (lo >= 0 && lo < ng && rk >= (int)s_pref[lo] && rk - (int)s_pref[lo] < __popc(s_live[lo])));
                 ci = active ? (gbeg + lo) * 32 + nth_set_bit(s_live[lo], (unsigned)(rk - (int)s_pref[lo])) : 0;
+                MPC_ASSERT(!active || ci < cand_cnt);
             }
             unsigned done = 0;
             // library record of the lane's candidate: sorted sets have their own copy of the library in set order
@@ -886,6 +898,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const __grid_co
                     if (has) {
                         const int k = __clz(hits);
                         hits &= ~(0x80000000u >> k);
+                        MPC_ASSERT(qn + __popc(bal) <= (unsigned)QCAP && base + k < 0x10000);
                         sq[qn + __popc(bal & lt_mask)] = ((unsigned)lane << 16) | (unsigned)(base + k);
                     }
                     qn += __popc(bal);
@@ -908,6 +921,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const __grid_co
                 unsigned ent;
                 const bool have = pop_batch(ent);
                 const int src = ent >> 16, slot = ent & 0xffff;
+                MPC_ASSERT(!have || (src < 32 && slot < p.cap_o));
                 float sep = BIG;
                 if (have) {
                     PolyRegs<VA> A;
@@ -927,6 +941,7 @@ __global__ void __launch_bounds__(K_THREADS, K_MIN_CTAS) k_check(const __grid_co
                 unsigned ent;
                 const bool have = pop_batch(ent);
                 const int src = ent >> 16, k = ent & 0xffff;
+                MPC_ASSERT(!have || (src < 32 && k < p.cap_s));
                 float sep = BIG;
                 if (have) {
                     PolyRegs<VA> A;
@@ -1418,6 +1433,7 @@ __device__ __forceinline__ void refine_pass(const KParams &p, const unsigned war
         const QDev *Q = p.q + q;
         const int pj = p.cand[Q->cand_base + ci] * p.J + j;
         const int nA = p.lib_nv[pj];
+        MPC_ASSERT(q >= 0 && q < p.B && ci >= 0 && ci < Q->cand_cnt && j < p.J && nA >= 3 && nA <= MPC_MAX_LIB_VERTS);
         __syncwarp();
         if ((int)lane < nA) {
             const double *lv = p.lib_v64 + ((size_t)pj * p.lib_vmax + lane) * 2;
@@ -1428,6 +1444,7 @@ __device__ __forceinline__ void refine_pass(const KParams &p, const unsigned war
         bool collide = false;
         if (kind == KIND_OBST) {
             const int nB = p.ob_nv[obj];
+            MPC_ASSERT(obj >= 0 && obj < p.ob_stride && nB >= 3 && nB <= MPC_MAX_OBST_VERTS);
             if ((int)lane < nB) {
                 const double *bv = p.ob_v64 + ((size_t)obj * p.ob_vmax + lane) * 2;
                 Bx[lane] = bv[0]; By[lane] = bv[1];
