@@ -81,6 +81,7 @@ struct KParams {
     const int2 *cta_tab;         // [c_total] (query, chunk) of every CTA of one time slot, built by the host with the batch
     const int *cand, *cand_pos, *cand_inv;      // cand_pos: sorted -> caller's position in the set, cand_inv: back
     int B, nwords;
+    int wmax, any_sorted;        // most result words of one query; some query uses a spatially sorted candidate set
     unsigned *mask;              // result bits, caller's candidate order
     unsigned *mask_sorted;       // result bits of spatially sorted candidate sets, un-permuted by k_refine
     int4 *wl;
@@ -1409,16 +1410,15 @@ __device__ __forceinline__ void refine_pass(const KParams &p, const unsigned war
     // phase A: result bits of spatially sorted candidate sets go home to the caller's candidate order.  One warp per
     // destination mask word: lane = candidate, which looks up its position in the sorted set and fetches its bit (a
     // gather: no atomics, no serial chain per word); one OR per word merges with the bits phase B adds below.
-    for (unsigned w = warp0; w < (unsigned)p.nwords; w += warps) {
-        int lo = 0, hi = p.B;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (p.q[mid].mask_off <= (int)w) lo = mid; else hi = mid;
-        }
-        while (lo + 1 < p.B && p.q[lo + 1].mask_off <= (int)w) lo++;     // queries without candidates share an offset
-        const QDev *Q = p.q + lo;
-        if (Q->pos_base < 0) continue;                                    // caller's order already
-        const int ci = ((int)w - Q->mask_off) * 32 + (int)lane;
+    // (query, word) pairs are enumerated arithmetically -- B x wmax slots, the ones beyond a query's own words are empty --
+    // instead of searching the query of every word; batches without sorted sets skip the phase
+    const unsigned long long slots = p.any_sorted ? (unsigned long long)p.B * (unsigned)p.wmax : 0ull;
+    for (unsigned long long idx = warp0; idx < slots; idx += warps) {
+        const int qi = (int)(idx / (unsigned)p.wmax), wq = (int)(idx - (unsigned long long)qi * (unsigned)p.wmax);
+        const QDev *Q = p.q + qi;
+        if (Q->pos_base < 0 || wq * 32 >= Q->cand_cnt) continue;          // caller's order already / no such word
+        const unsigned w = (unsigned)(Q->mask_off + wq);
+        const int ci = wq * 32 + (int)lane;
         bool bit = false;
         if (ci < Q->cand_cnt) {
             const int sp = __ldg(p.cand_inv + Q->pos_base + ci);          // position of candidate ci in the sorted set

@@ -95,6 +95,7 @@ struct mpc_ctx {
     void *res_p = nullptr;        // result block of the prepared batch: inside qpack_d (fused_clear) or res_d
     bool fused_clear = false;     // small result blocks are cleared by the zeros the query upload carries
     size_t qpack_cta_off = 0, qpack_cta2_off = 0, qpack_hdr_off = 0, up_bytes = 0, up_cand_bytes = 0, up_cand_src = 0;
+    int wmax = 1, any_sorted = 0; // most result words of one query of the batch; some query uses a sorted candidate set
     int wsplit = 1;               // warps per candidate group in k_check (few groups per CTA)
     bool tail = false;            // prepared batch runs as ONE kernel: refinement + result hand-over in the last CTA of k_check
     volatile unsigned *h_flag = nullptr;      // page-locked word the tail raises
@@ -855,6 +856,7 @@ static KParams make_params(mpc_ctx *ctx) {
     p.cand_pos = (const int *)ctx->sets_pos.p;
     p.cand_inv = p.cand_pos + ctx->set_total;
     p.B = ctx->B;
+    p.wmax = ctx->wmax; p.any_sorted = ctx->any_sorted;
     p.cnt = (Counters *)ctx->res_p; p.mask = (unsigned *)((char *)ctx->res_p + sizeof(Counters));
     p.mask_sorted = p.mask + ctx->mask_words;
     p.nwords = ctx->mask_words;
@@ -1108,6 +1110,7 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
     int *hidx = (int *)((char *)ctx->h_pin + cand_src);
     long long ctas = 0, words = 0, c2 = 0;
     double maxq = 0.0;
+    int wmax = 1, any_sorted = 0;
     for (int q = 0; q < B; q++) {
         const mpc_query_desc &d = queries[q];
         QDev &o = hq[q];
@@ -1130,6 +1133,8 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
         o.cand_cnt = d.cand_cnt;
         o.mask_off = (int)words;
         const int groups = (d.cand_cnt + 31) / 32;
+        wmax = std::max(wmax, groups);
+        any_sorted |= o.pos_base >= 0;
         o.chunks = std::max(1, (groups + gpc - 1) / gpc);
         if (groups) {                              // per time slot: the grid is slot-major, ctas * J blocks in all
             for (int c = 0; c < o.chunks; c++) htab[ctas + c] = make_int2(q, c);
@@ -1182,6 +1187,7 @@ static int prepare_host(mpc_ctx *ctx, int B, const mpc_query_desc *queries, cons
     CU(ensure_result_host(ctx, sizeof(Counters) + sizeof(unsigned) * (size_t)std::max<long long>(words, 1)));
     ctx->res_p = fused ? (void *)((char *)ctx->qpack_d.p + zoff) : ctx->res_d.p;
     ctx->B = B; ctx->ctas = (int)ctas; ctx->mask_words = (int)words; ctx->mode = mode;
+    ctx->wmax = wmax; ctx->any_sorted = any_sorted;
     ctx->prepared = true;
     if (upload) return issue_uploads(ctx);
     return MPC_OK;
@@ -1262,7 +1268,7 @@ static int run_once(mpc_ctx *ctx, float *ms, int *kernels, int *overflow, bool t
 static int run_graph(mpc_ctx *ctx, float *ms, bool timed, bool sync = true) {
     const size_t bytes = sizeof(Counters) + (size_t)ctx->mask_words * sizeof(unsigned);
     const bool tail = ctx->tail && ctx->ctas > 0;
-    std::vector<long long> key = {(long long)ctx->B, (long long)ctx->ctas, (long long)ctx->scouts * 1000 + ctx->scout_gpc + 10000000LL * ctx->wsplit, (long long)ctx->scout_c_total, (long long)ctx->fused_clear + 2 * (long long)tail, (long long)ctx->mask_words, (long long)ctx->mode,
+    std::vector<long long> key = {(long long)ctx->B, (long long)ctx->ctas, (long long)ctx->scouts * 1000 + ctx->scout_gpc + 10000000LL * ctx->wsplit, (long long)ctx->scout_c_total, (long long)ctx->fused_clear + 2 * (long long)tail + 4 * (long long)ctx->any_sorted + 8LL * ctx->wmax, (long long)ctx->mask_words, (long long)ctx->mode,
                                   (long long)ctx->gpc, (long long)ctx->cap_o, (long long)ctx->cap_s, (long long)ctx->smem,
                                   (long long)ctx->up_bytes, (long long)ctx->up_cand_bytes, (long long)ctx->wl_cap,
                                   (long long)ctx->VA, (long long)ctx->VB, (long long)ctx->ob_stride, (long long)ctx->sg_stride,
