@@ -203,6 +203,51 @@ def test_multiple_scenes_in_one_batch(eng):
         o += n
 
 
+def test_mixed_regime_full_size(eng):
+    """the non-degenerate regime of bench.py (`regimes.mixed`: same 4096 x 256 x 50 shape, 35 % of the candidates are
+    free and need every time step) at full size against the oracle, in every launch mode bench.py times it in, and
+    through the asynchronous cycle (mpc_submit / mpc_wait)"""
+    lib, sc, org, q = W.mixed_traffic_problem(nqueries=6)
+    stage(eng, lib, sc, org)
+    pb = orc.Problem(lib, sc)
+    want, ost = pb.check(q, None, 0, inner_parallel=True)
+    assert 0.25 < 1.0 - want.mean() < 0.5                        # the regime: 30-50 % free candidates
+    got, st = eng.query(q, None, MODE_PLANNER)
+    assert st["pairs_nominal"] == 6 * 4096 * 50 * (256 + 4) == ost["pairs_nominal"]
+    assert np.array_equal(got, want)
+    got_ne, _ = eng.query(q, None, MODE_PLANNER | MODE_NO_EARLY_EXIT)          # `cull_only`
+    assert np.array_equal(got_ne, want)
+    got_full, _ = eng.query(q[:2], None, MODE_NO_CULL | MODE_NO_EARLY_EXIT)    # `full_evaluation` (k_check_full)
+    assert np.array_equal(got_full, want[:2 * 4096])
+    wantv, _ = pb.check(q, None, orc.MODE_STRICT, inner_parallel=True)
+    gotv, _ = eng.query(q, None, MODE_VALIDATOR)
+    assert np.array_equal(gotv, wantv)
+    keys = ("scene_step_off", "origins", "step_obst_off", "obst", "obst_nv", "step_seg_begin", "step_seg_end", "segs")
+    eng.submit(CollisionEngine.scene_args(*[dict(sc, origins=org)[k] for k in keys]), q, MODE_PLANNER)
+    mask, _ = eng.wait()
+    from motionplanner_b200.engine import unpack_mask
+    assert np.array_equal(unpack_mask(mask, q), want)
+
+
+@pytest.mark.parametrize("obst_verts", [4, 8])
+def test_aroc_shaped_library_against_oracle(eng, obst_verts):
+    """the many-vertex instantiations bench.py measures (`aroc_shaped`: 12-vertex convex occupancies over time intervals,
+    two scenes per query as for interval automata; k_check<16,4> / <16,8>) against the oracle, default mode and full
+    evaluation"""
+    lib, sc, org, q = W.aroc_shaped_problem(P=1024, T=10, nqueries=4, obst_verts=obst_verts)
+    stage(eng, lib, sc, org)
+    pb = orc.Problem(lib, sc)
+    want, ost = pb.check(q, None, orc.MODE_NO_EARLY_EXIT)
+    got, st = eng.query(q, None, MODE_PLANNER)
+    assert np.array_equal(got, want) and st["pairs_nominal"] == ost["pairs_nominal"]
+    assert 0.0 < want.mean() < 1.0
+    got_full, _ = eng.query(q[:2], None, MODE_NO_CULL | MODE_NO_EARLY_EXIT)
+    assert np.array_equal(got_full, want[:2 * 1024])
+    wantv, _ = pb.check(q, None, orc.MODE_STRICT | orc.MODE_NO_EARLY_EXIT)
+    gotv, _ = eng.query(q, None, MODE_VALIDATOR)
+    assert np.array_equal(gotv, wantv)
+
+
 def test_c4_dense_traffic_full_size(eng):
     """BASELINE.json configs[3] at full size (4096 x 256 x 50 = 52.4 M pairs per query) against the oracle, plus
     size-independent properties: idempotence and invariance under an exact rigid motion of the whole problem"""
