@@ -301,7 +301,7 @@ class PrimitiveChecker:
     def bucket_collides(self, x, y, phi, t0, step_limit, bucket, scenes=(0,)):
         """collision bits (True = collides) of every primitive of velocity bucket `bucket` appended at pose
         (x, y, phi) and time index t0; with several scenes a candidate collides if it does in any of them"""
-        if getattr(self.backend, '_scene_owner', None) is not self or self.backend._staged_library != self._lib_key:
+        if getattr(self.backend, '_scene_owner', None) is not self or getattr(self.backend, '_staged_library', None) != self._lib_key:
             self._ensure_staged()
         cnt = self._set_len_list[bucket]
         ns = len(scenes)

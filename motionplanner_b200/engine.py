@@ -226,6 +226,8 @@ class CollisionEngine:
 
     def wait(self, want_stats=True):
         """result of the submitted batch: (packed mask [copy], stats dict or None)"""
+        if getattr(self, "_inflight", None) is None:
+            raise MpcError("wait() without a submitted batch")
         nw = self._inflight[3]
         mask = np.empty(max(nw, 1), dtype=np.uint32)
         st = _cabi.Stats() if want_stats else None
