@@ -77,6 +77,7 @@ struct mpc_ctx {
     bool have_scenes = false;
     int nscenes = 0, nsteps = 0, nobst = 0, nseg = 0, ob_vmax = 4, VB = 4, max_obst_step = 0, max_seg_step = 0;
     std::vector<int> scene_step_off;
+    std::vector<const void *> known_pinned;       // host addresses cudaPointerGetAttributes reported as page-locked
     std::vector<double> origins;
     DevBuf ob_src, ob_src_nv, ob_src_off, ob_c, ob_box, ob_order, step_obst_cnt, sets_pos;
     int ob_stride = 32;
@@ -277,7 +278,10 @@ extern "C" int mpc_alloc_pinned(mpc_ctx *ctx, uint64_t bytes, void **out) {
 
 extern "C" int mpc_free_pinned(mpc_ctx *ctx, void *ptr) {
     if (!ctx || !ctx->stream) return MPC_E_ARG;
-    if (ptr) CU(cudaFreeHost(ptr));
+    if (ptr) {
+        ctx->known_pinned.erase(std::remove(ctx->known_pinned.begin(), ctx->known_pinned.end(), (const void *)ptr), ctx->known_pinned.end());
+        CU(cudaFreeHost(ptr));
+    }
     return MPC_OK;
 }
 
@@ -544,10 +548,19 @@ static int set_scenes_impl(mpc_ctx *ctx, int nscenes, const int32_t *scene_step_
     const bool seg_dev_wanted = nseg >= 8192;
     // A small scene in page-locked arrays (a planner re-staging its prediction every cycle) is staged by replaying a
     // captured graph: one driver call instead of eight.  Everything the nodes hold is in the key below.
-    auto pinned = [](const void *ptr) {
+    // (the answer is remembered per address: the query costs 1-3 us, twice per call.  A stale "page-locked" for memory
+    // that was freed and came back pageable only makes the replayed copy node slower, not wrong)
+    auto pinned = [ctx](const void *ptr) {
+        for (const void *known : ctx->known_pinned)
+            if (known == ptr) return true;
         cudaPointerAttributes a;
         if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
-        return a.type == cudaMemoryTypeHost;
+        const bool is = a.type == cudaMemoryTypeHost;
+        if (is) {
+            if (ctx->known_pinned.size() >= 64) ctx->known_pinned.clear();
+            ctx->known_pinned.push_back(ptr);
+        }
+        return is;
     };
     static const bool no_scene_graph = getenv("MPC_NO_SCENE_GRAPH") != nullptr;
     const bool use_graph = !no_scene_graph && !seg_dev_wanted && (size_t)nobst * Vo * 2 * sizeof(double) <= ((size_t)4 << 20) &&
