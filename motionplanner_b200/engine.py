@@ -5,6 +5,7 @@ Reference being replaced: the per-occupancy shapely loop of ``collision_check``
 (src/lowLevelPlannerManeuverAutomaton.py:95-125) and ``collisionChecker`` (auxiliary/collisionChecker.py:6-35).
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -19,8 +20,9 @@ __all__ = ["CollisionEngine", "QUERY_DTYPE", "MODE_PLANNER", "MODE_VALIDATOR", "
 _I4, _F8 = np.dtype(np.int32), np.dtype(np.float64)
 
 # data address of an ndarray, remembered per array OBJECT: a producer refills the same (page-locked) arrays every cycle,
-# and `a.ctypes.data` costs 1.1 us per array, nine arrays per cycle.  The entry holds the array itself (its id cannot be
-# reused while it sits here) and its shape (an in-place resize is the only way a live array's buffer moves).
+# and `a.ctypes.data` costs 1.1 us per array, nine arrays per cycle.  The entry holds a weak reference (a dead array's
+# id may be reused: the reference then no longer resolves to the caller's array) and the shape (an in-place resize is
+# the only way a live array's buffer moves); nothing is kept alive by the table.
 _PTRS = {}
 
 
@@ -28,12 +30,15 @@ def _addr(a):
     if a is None or a.size == 0:
         return None
     ent = _PTRS.get(id(a))
-    if ent is not None and ent[0] is a and ent[1] == a.shape:
+    if ent is not None and ent[0]() is a and ent[1] == a.shape:
         return ent[2]
     if len(_PTRS) >= 256:
         _PTRS.clear()
     p = a.ctypes.data
-    _PTRS[id(a)] = (a, a.shape, p)
+    try:
+        _PTRS[id(a)] = (weakref.ref(a), a.shape, p)
+    except TypeError:                 # an ndarray subclass without weak references
+        pass
     return p
 
 
