@@ -9,11 +9,17 @@
  *   - every function returns 0 on success or a negative MPC_E_* code; nothing throws across the ABI;
  *     mpc_last_error(ctx) gives a human-readable message for the last failure on that context.
  *   - the caller owns all host buffers (plain pointers + sizes, little-endian, C order); the library owns all device
- *     memory.  Host buffers may be reused as soon as a call returns.
+ *     memory.  Host buffers may be reused as soon as a call returns -- with one exception: the buffers handed to
+ *     mpc_submit stay in use until the matching mpc_wait has returned.
  *   - one context <=> one device + one CUDA stream.  A context is not thread-safe; contexts are independent (one per
  *     GPU, one process per GPU in the multi-GPU harness) and share no mutable state, so several contexts on the SAME
- *     device may be driven from different host threads at once: the copies and staging kernels of one overlap the
- *     check kernels of another (motionplanner_b200/lanes.py).  Calls do not hold the Python GIL (ctypes releases it).
+ *     device may be driven from different host threads at once, or from ONE thread through the asynchronous pair
+ *     mpc_submit / mpc_wait: the copies and staging kernels of one overlap the check kernels of another
+ *     (motionplanner_b200/lanes.py).  Calls do not hold the Python GIL (ctypes releases it).
+ *   - polygons must be CONVEX (occupancy polygons of the library, obstacle pieces of a scene): the separating-axis
+ *     test is only correct for convex sets -- a reflex edge would "separate" what it must not.  Non-convex input is
+ *     rejected with MPC_E_ARG (library: at upload; obstacle pieces: by the staging kernel, reported by
+ *     mpc_set_scenes / mpc_wait); repeated vertices are tolerated.  Decompose first (checker.convex_pieces).
  *   - all geometry comes in as float64 in the caller's global frame, exactly the numbers the reference hands to
  *     shapely.  Re-centring to a scene-local frame and the float32 cast happen inside, on the device.
  *   - decisions are exact with respect to those float64 vertices: a float32 separating-axis pass with a conservative
@@ -29,7 +35,7 @@
 extern "C" {
 #endif
 
-#define MPC_ABI_VERSION 2
+#define MPC_ABI_VERSION 3      /* 3: mpc_submit / mpc_wait, mpc_measure_fp32_peak, convexity is checked */
 
 /* error codes */
 #define MPC_OK 0
